@@ -1,0 +1,154 @@
+/* deepsent.h — C ABI of libdeepsent.so: the sm_100a kernels behind the Deep Sentiment
+ * joint training step of anthonyhu/tumblr-emotions.
+ *
+ * The reference has no FFI/plugin boundary of its own: every op below is the
+ * replacement of a TensorFlow-1.x op *site* in the reference's Python graph code; the site is
+ * cited beside each entry point (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; ds_last_error() returns the
+ *     thread-local message.  Nothing throws or aborts.
+ *   - all tensor arguments are raw DEVICE pointers (fp32 unless stated), followed by explicit
+ *     int64 dims / leading dimensions (in elements); `stream` is a cudaStream_t.
+ *   - no ownership transfer, no hidden allocation, no hidden synchronisation: every launch is
+ *     asynchronous on `stream` (CUDA-graph capturable).
+ *   - activations are NHWC; "ld" of an activation is the element stride between two pixels, so
+ *     a channel slice of a concat buffer is (ptr + channel_offset, ld = total channels).
+ */
+#ifndef DEEPSENT_H_
+#define DEEPSENT_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------- */
+int ds_version(void);
+const char* ds_last_error(void);
+/* binds the calling thread to `device`, resolves cuTensorMapEncode{Tiled,Im2col}, caches SM count */
+int ds_init(int device);
+int ds_sm_count(void);
+/* development knobs (0 = default): key 0 = im2col base-coordinate convention, 1 = force N tile, 2 = force stages,
+ * 3 = shared-memory budget per CTA in KB */
+int ds_debug_set(int key, int value);
+int ds_debug_get(int key);
+
+/* ---- dense contractions ---------------------------------------------------------------- */
+/* flags for the contraction epilogues */
+#define DS_EPI_RELU 1        /* out = max(out, 0)                        */
+#define DS_EPI_ACCUMULATE 2  /* out += previous contents of C            */
+#define DS_EPI_STATS 4       /* also add per-column sum / sum-of-squares into stats[2*N] (double) */
+
+/* tcgen05 TF32 implicit GEMM (TMA-staged smem tiles, TMEM accumulator), stride 1, TF-"SAME":
+ *   C[m, n] = epi( sum_{r,s,c} A[pixel(m) + (r-p, s-p), c] * Bt[n, (r*ks+s)*cin + c] )
+ * A: NHWC activation slice [batch, h, w, cin] with pixel stride lda (1x1: plain [M,K] GEMM; 3x3:
+ * TMA im2col mode).  Bt: K-major weights [N, ks*ks*cin] with row stride ldb.  C: [M, ldc].
+ * epi: acc*scale[n] + bias[n] (either may be NULL), then flags.
+ * Replaces slim.conv2d 1x1/3x3 sites image_model/inception_v1.py:71-247 (fwd) and their
+ * tf.gradients input-gradient (Conv2DBackpropInput == same contraction on flipped weights), the
+ * LSTM projections text_model/text_embedding.py:79-80, image_text_model/im_text_rnn_model.py:89-90.
+ * Requirements: cin % 8 == 0, n % 4 == 0, lda/ldb/ldc % 4 == 0, 16-byte aligned bases. */
+int ds_conv_tc(const float* a, int64_t lda, int64_t batch, int64_t h, int64_t w, int64_t cin, int ksize,
+               const float* bt, int64_t ldb, int64_t n, float* c, int64_t ldc,
+               const float* scale, const float* bias, double* stats, int flags, void* stream);
+
+/* SIMT fp32 convolution (any k, stride, explicit TF-SAME pads): the 7x7/2 stem
+ * (image_model/inception_v1.py:63) and the fp32 cross-check path.  w_kn: HWIO == [kh*kw*cin, n]. */
+int ds_conv_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t cin,
+                 int kh, int kw, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
+                 const float* w_kn, int64_t ldw, int64_t n, float* y, int64_t ldy,
+                 const float* bias, int flags, void* stream);
+
+/* SIMT fp32 strided GEMM: C[m,n] = epi( sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + bias[n] ).
+ * Small/odd-shaped products: FC + softmax layers (im_text_rnn_model.py:98-105), Logits 1x1
+ * (inception_v1.py:302-303), their gradients. */
+int ds_gemm_simt(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbk, int64_t sbn,
+                 float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, const float* bias, int flags,
+                 void* stream);
+
+/* conv weight-gradient (Conv2DBackpropFilter) for the trainable Mixed_5c convs
+ * (image_model/inception_v1.py:229-248):  dW[(r,s,c), n] (+)= sum_m X[pix(m)+(r,s), c] * dZ[m, n] */
+int ds_conv_wgrad_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t cin,
+                       int kh, int kw, int pad_t, int pad_l, const float* dz, int64_t lddz, int64_t n,
+                       float* dw, int64_t lddw, int flags, void* stream);
+
+/* out[c, r] = in[r, c] */
+int ds_transpose(const float* in, int64_t ldin, int64_t rows, int64_t cols, float* out, int64_t ldout, void* stream);
+/* HWIO [kh,kw,cin,cout] -> forward operand [cout][kh][kw][cin] and input-gradient operand
+ * [cin][kh'][kw'][cout] (taps flipped; row (ci,r',s') has stride dgrad_ld so sibling 1x1 convs can share one fused operand), both
+ * optionally rounded to TF32 (round-to-nearest). */
+int ds_repack_conv_weights(const float* hwio, int kh, int kw, int64_t cin, int64_t cout,
+                           float* fwd_ohwi, float* dgrad_ihwo, int64_t dgrad_ld, int round_tf32, void* stream);
+
+/* ---- batch norm (slim.batch_norm center=True scale=False; slim/nets/inception_utils.py:48-70) */
+/* stats[0:N] += column sums of z, stats[N:2N] += column sums of z^2 (double accumulators) */
+int ds_colstats(const float* z, int64_t ldz, int64_t m, int64_t n, double* stats, void* stream);
+/* training: mean/var from stats (biased), y = relu((z-mean)*rsqrt(var+eps)+beta); writes mean/rstd
+ * for the backward pass and applies moving <- moving - momentum*(moving - batch).
+ * inference (stats == NULL): uses moving_mean / moving_var.   flags: DS_BN_TF32 rounds y to TF32,
+ * DS_BN_UNBIASED feeds the unbiased variance to the moving average, DS_BN_NO_RELU skips the ReLU */
+#define DS_BN_TF32 1
+#define DS_BN_UNBIASED 2
+#define DS_BN_NO_RELU 4
+int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const double* stats,
+                     const float* beta, float* moving_mean, float* moving_var, float momentum, float eps,
+                     float* mean_out, float* rstd_out, float* y, int64_t ldy, int flags, void* stream);
+/* backward of relu(bn(z)): g = dy*[bn(z)>0]; sums[0:N] += sum g, sums[N:2N] += sum g*xhat */
+int ds_bn_relu_bwd_reduce(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
+                          const float* mean, const float* rstd, const float* beta, double* sums, void* stream);
+/* dz = rstd*(g - sum(g)/m - xhat*sum(g*xhat)/m) written over z; dbeta[n] = sum g; DS_BN_TF32 rounds dz */
+int ds_bn_relu_bwd_apply(const float* dy, int64_t lddy, float* z, int64_t ldz, int64_t m, int64_t n,
+                         const float* mean, const float* rstd, const float* beta, const double* sums,
+                         float* dbeta, int flags, void* stream);
+
+/* ---- pooling (slim.max_pool2d / avg_pool2d / dropout, image_model/inception_v1.py:67,79,94,118,208,299-302) */
+int ds_maxpool_fwd(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c, int k, int stride,
+                   int pad_t, int pad_l, int64_t ho, int64_t wo, float* y, int64_t ldy, uint8_t* argmax, void* stream);
+int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t batch, int64_t h, int64_t w,
+                   int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
+                   float* dx, int64_t lddx, int accumulate, void* stream);
+/* out[b,c] = mean_p x[b,p,c] * (mask ? mask[b,c]*inv_keep : 1) */
+int ds_avgpool_dropout_fwd(const float* x, int64_t ldx, int64_t batch, int64_t hw, int64_t c, const float* mask,
+                           float inv_keep, float* out, int64_t ldo, void* stream);
+int ds_avgpool_dropout_bwd(const float* dout, int64_t ldo, int64_t batch, int64_t hw, int64_t c, const float* mask,
+                           float inv_keep, float* dx, int64_t lddx, void* stream);
+/* counter-based Bernoulli(keep) mask in {0,1}; *counter (device) is incremented by the kernel */
+int ds_dropout_mask(float* mask, int64_t n, float keep, uint64_t seed, uint64_t* counter, void* stream);
+
+/* ---- text tower (tf.nn.embedding_lookup + BasicLSTMCell/dynamic_rnn, im_text_rnn_model.py:82-92) */
+/* out[(t*batch + b), 0:dim] = table[ids[b,t], :], columns dim..ldo-1 zero-filled (bit-exact gather) */
+int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const int64_t* ids, int64_t batch,
+                        int64_t steps, float* out, int64_t ldo, void* stream);
+/* one time step.  pre = zh + xw + bias, gate order i,j,f,o (BasicLSTMCell): c' = c*sig(f+fb)+sig(i)*tanh(j),
+ * h' = tanh(c')*sig(o); rows with t >= seq_len carry (c,h) (dynamic_rnn semantics).  Saves the gate
+ * activations [batch,4n] for BPTT. */
+int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const float* c_prev, const float* h_prev,
+                      const int64_t* seq_len, int64_t t, int64_t batch, int64_t n, float forget_bias,
+                      float* gates, float* c_out, float* h_out, int round_tf32, void* stream);
+/* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n]; updates carries */
+int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len,
+                      int64_t t, int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc,
+                      float* dz, int round_tf32, void* stream);
+
+/* ---- head / loss / optimiser ------------------------------------------------------------ */
+/* slim.losses.softmax_cross_entropy (im_text_rnn_model.py:124-125): loss_rows[b], dlogits = (p - onehot)*scale */
+int ds_softmax_xent(const float* logits, int64_t ldl, const int64_t* labels, int64_t batch, int64_t classes,
+                    float scale, float* loss_rows, float* dlogits, int64_t lddl, void* stream);
+/* out[0] (+)= scale * sum(x[0:n])   (single CTA, deterministic) */
+int ds_reduce_sum(const float* x, int64_t n, float scale, float* out, int accumulate, void* stream);
+/* out[0] (+)= scale * sum(x^2): slim.l2_regularizer(4e-5) term of get_total_loss (inception_utils.py:32,56) */
+int ds_sumsq(const float* x, int64_t n, float scale, float* out, int accumulate, void* stream);
+/* out[n] (+)= sum_m x[m,n]  (bias gradients) */
+int ds_colsum(const float* x, int64_t ldx, int64_t m, int64_t n, float* out, int accumulate, void* stream);
+int ds_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
+/* dy *= (y > 0) */
+int ds_relu_bwd(float* dy, const float* y, int64_t n, void* stream);
+int ds_round_tf32(float* x, int64_t n, void* stream);
+/* tf.train.AdamOptimizer (im_text_rnn_model.py:134): hyper (device) = {lr_t, beta1, beta2, eps, grad_scale};
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps), lr_t pre-corrected by the host */
+int ds_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSENT_H_ */

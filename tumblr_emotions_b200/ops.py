@@ -1,0 +1,196 @@
+"""Thin Python wrappers over the C ABI: torch tensors are only containers for device memory.
+
+A `View` is a 2-D window [rows, cols] with row stride `ld` over an fp32 buffer - e.g. one branch's channel
+slice of an inception block's concat output.  Every wrapper launches on torch's current CUDA stream, so the
+whole step can be captured into a CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib
+
+EPI_RELU, EPI_ACCUMULATE, EPI_STATS = 1, 2, 4
+BN_TF32, BN_UNBIASED, BN_NO_RELU = 1, 2, 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int:
+    if t is None:
+        return 0
+    if isinstance(t, View):
+        return t.ptr
+    return t.data_ptr()
+
+
+class View:
+    """[rows, cols] fp32 window with row stride ld (elements) starting `coff` columns into `base`."""
+    __slots__ = ("base", "rows", "cols", "ld", "coff")
+
+    def __init__(self, base: torch.Tensor, cols: int = None, coff: int = 0, ld: int = None):
+        assert base.dtype == torch.float32 and base.is_contiguous()
+        self.base = base
+        self.ld = int(ld if ld is not None else base.shape[-1])
+        self.rows = base.numel() // self.ld
+        self.coff = int(coff)
+        self.cols = int(cols if cols is not None else self.ld - coff)
+
+    @property
+    def ptr(self) -> int:
+        return self.base.data_ptr() + 4 * self.coff
+
+    def slice(self, coff: int, cols: int) -> "View":
+        return View(self.base, cols, self.coff + coff, self.ld)
+
+    def torch(self) -> torch.Tensor:
+        return self.base.view(self.rows, self.ld)[:, self.coff:self.coff + self.cols]
+
+
+def init(device: int = 0):
+    lib().init(device)
+
+
+# ---- contractions -------------------------------------------------------------------------------
+def conv_tc(a: View, batch, h, w, cin, ksize, bt, ldb, n, c: View, scale=None, bias=None, stats=None, flags=0):
+    if stats is not None:
+        flags |= EPI_STATS
+    lib().conv_tc(a.ptr, a.ld, batch, h, w, cin, ksize, _p(bt), ldb, n, c.ptr, c.ld, _p(scale), _p(bias), _p(stats), flags,
+                  _stream())
+
+
+def gemm_tc(a: View, bt, ldb, n, c: View, k=None, bias=None, flags=0):
+    """C[rows, n] = A[rows, k] x Bt[n, k]^T on the tensor cores."""
+    conv_tc(a, a.rows, 1, 1, k if k is not None else a.cols, 1, bt, ldb, n, c, None, bias, None, flags)
+
+
+def conv_simt(x: View, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, w_kn, n, y: View, bias=None, flags=0):
+    lib().conv_simt(x.ptr, x.ld, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, _p(w_kn), n, n, y.ptr, y.ld,
+                    _p(bias), flags, _stream())
+
+
+def gemm_simt(a_ptr, sam, sak, b_ptr, sbk, sbn, c: View, m, n, k, bias=None, flags=0):
+    lib().gemm_simt(a_ptr, sam, sak, b_ptr, sbk, sbn, c.ptr, c.ld, m, n, k, _p(bias), flags, _stream())
+
+
+def gemm_nn(a: View, b: View, c: View, bias=None, flags=0):
+    """C = A[m,k] x B[k,n]"""
+    gemm_simt(a.ptr, a.ld, 1, b.ptr, b.ld, 1, c, a.rows, b.cols, a.cols, bias, flags)
+
+
+def gemm_nt(a: View, b: View, c: View, bias=None, flags=0):
+    """C = A[m,k] x B[n,k]^T"""
+    gemm_simt(a.ptr, a.ld, 1, b.ptr, 1, b.ld, c, a.rows, b.rows, a.cols, bias, flags)
+
+
+def gemm_tn(a: View, b: View, c: View, flags=0):
+    """C = A[k,m]^T x B[k,n]"""
+    gemm_simt(a.ptr, 1, a.ld, b.ptr, b.ld, 1, c, a.cols, b.cols, a.rows, None, flags)
+
+
+def conv_wgrad_simt(x: View, batch, h, w, cin, kh, kw, pad_t, pad_l, dz: View, n, dw: torch.Tensor, flags=0):
+    lib().conv_wgrad_simt(x.ptr, x.ld, batch, h, w, cin, kh, kw, pad_t, pad_l, dz.ptr, dz.ld, n, dw.data_ptr(), n, flags,
+                          _stream())
+
+
+def transpose(src: View, dst: View):
+    lib().transpose(src.ptr, src.ld, src.rows, src.cols, dst.ptr, dst.ld, _stream())
+
+
+def repack_conv_weights(hwio: torch.Tensor, fwd=None, dgrad=None, dgrad_ld=None, round_tf32=True):
+    kh, kw, cin, cout = hwio.shape
+    lib().repack_conv_weights(hwio.data_ptr(), kh, kw, cin, cout, _p(fwd), _p(dgrad),
+                              dgrad_ld if dgrad_ld is not None else cout, 1 if round_tf32 else 0, _stream())
+
+
+# ---- batch norm ---------------------------------------------------------------------------------
+def colstats(z: View, stats):
+    lib().colstats(z.ptr, z.ld, z.rows, z.cols, _p(stats), _stream())
+
+
+def bn_apply_relu(z: View, stats, beta, moving_mean, moving_var, momentum, eps, mean_out, rstd_out, y: View, flags=0):
+    lib().bn_apply_relu(z.ptr, z.ld, z.rows, z.cols, _p(stats), _p(beta), _p(moving_mean), _p(moving_var), momentum, eps,
+                        _p(mean_out), _p(rstd_out), y.ptr, y.ld, flags, _stream())
+
+
+def bn_relu_bwd_reduce(dy: View, z: View, mean, rstd, beta, sums):
+    lib().bn_relu_bwd_reduce(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), _stream())
+
+
+def bn_relu_bwd_apply(dy: View, z: View, mean, rstd, beta, sums, dbeta, flags=0):
+    lib().bn_relu_bwd_apply(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), _p(dbeta),
+                            flags, _stream())
+
+
+# ---- pooling -------------------------------------------------------------------------------------
+def maxpool_fwd(x: View, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, y: View, argmax=None):
+    lib().maxpool_fwd(x.ptr, x.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, y.ptr, y.ld, _p(argmax), _stream())
+
+
+def maxpool_bwd(dy: View, argmax, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, dx: View, accumulate=False):
+    lib().maxpool_bwd(dy.ptr, dy.ld, _p(argmax), batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, dx.ptr, dx.ld,
+                      1 if accumulate else 0, _stream())
+
+
+def avgpool_dropout_fwd(x: View, batch, hw, c, mask, inv_keep, out: View):
+    lib().avgpool_dropout_fwd(x.ptr, x.ld, batch, hw, c, _p(mask), inv_keep, out.ptr, out.ld, _stream())
+
+
+def avgpool_dropout_bwd(dout: View, batch, hw, c, mask, inv_keep, dx: View):
+    lib().avgpool_dropout_bwd(dout.ptr, dout.ld, batch, hw, c, _p(mask), inv_keep, dx.ptr, dx.ld, _stream())
+
+
+def dropout_mask(mask: torch.Tensor, keep: float, seed: int, counter: torch.Tensor):
+    lib().dropout_mask(mask.data_ptr(), mask.numel(), keep, seed, counter.data_ptr(), _stream())
+
+
+# ---- text ------------------------------------------------------------------------------------------
+def embedding_gather(table: torch.Tensor, ids: torch.Tensor, out: View):
+    b, t = ids.shape
+    lib().embedding_gather(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), b, t, out.ptr, out.ld, _stream())
+
+
+def lstm_gates_fwd(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, n, forget_bias, gates, c_out, h_out, round_tf32):
+    lib().lstm_gates_fwd(_p(zh), _p(xw), _p(bias), _p(c_prev), _p(h_prev), _p(seq_len), t, batch, n, forget_bias, _p(gates),
+                         _p(c_out), _p(h_out), 1 if round_tf32 else 0, _stream())
+
+
+def lstm_gates_bwd(gates, c_prev, c_cur, seq_len, t, batch, n, dh_rec, dh_carry, dc, dz, round_tf32):
+    lib().lstm_gates_bwd(_p(gates), _p(c_prev), _p(c_cur), _p(seq_len), t, batch, n, _p(dh_rec), _p(dh_carry), _p(dc), _p(dz),
+                         1 if round_tf32 else 0, _stream())
+
+
+# ---- head / loss / optimiser ---------------------------------------------------------------------
+def softmax_xent(logits: View, labels, scale, loss_rows, dlogits: View):
+    lib().softmax_xent(logits.ptr, logits.ld, _p(labels), logits.rows, logits.cols, scale, _p(loss_rows),
+                       dlogits.ptr if dlogits is not None else 0, dlogits.ld if dlogits is not None else 0, _stream())
+
+
+def reduce_sum(x: torch.Tensor, scale, out, accumulate=False):
+    lib().reduce_sum(x.data_ptr(), x.numel(), scale, _p(out), 1 if accumulate else 0, _stream())
+
+
+def sumsq(x: torch.Tensor, scale, out, accumulate=False):
+    lib().sumsq(x.data_ptr(), x.numel(), scale, _p(out), 1 if accumulate else 0, _stream())
+
+
+def colsum(x: View, out, accumulate=False):
+    lib().colsum(x.ptr, x.ld, x.rows, x.cols, _p(out), 1 if accumulate else 0, _stream())
+
+
+def axpy(y: torch.Tensor, x: torch.Tensor, alpha: float):
+    lib().axpy(y.data_ptr(), x.data_ptr(), alpha, y.numel(), _stream())
+
+
+def relu_bwd(dy: torch.Tensor, y: torch.Tensor):
+    lib().relu_bwd(dy.data_ptr(), y.data_ptr(), y.numel(), _stream())
+
+
+def round_tf32(x: torch.Tensor):
+    lib().round_tf32(x.data_ptr(), x.numel(), _stream())
+
+
+def adam(p, g, m, v, hyper):
+    lib().adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), hyper.data_ptr(), _stream())
