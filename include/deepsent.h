@@ -53,10 +53,11 @@ int ds_conv_tc(const float* a, int64_t lda, int64_t batch, int64_t h, int64_t w,
                const float* scale, const float* bias, double* stats, int flags, void* stream);
 
 /* SIMT fp32 convolution (any k, stride, explicit TF-SAME pads): the 7x7/2 stem
- * (image_model/inception_v1.py:63) and the fp32 cross-check path.  w_kn: HWIO == [kh*kw*cin, n]. */
+ * (image_model/inception_v1.py:63) and the fp32 cross-check path.  Weight element ((r*kw+s)*cin+c, n) is read at
+ * wgt[kidx*swk + n*swn]: HWIO is (swk=n, swn=1). */
 int ds_conv_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t cin,
                  int kh, int kw, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
-                 const float* w_kn, int64_t ldw, int64_t n, float* y, int64_t ldy,
+                 const float* wgt, int64_t swk, int64_t swn, int64_t n, float* y, int64_t ldy,
                  const float* bias, int flags, void* stream);
 
 /* SIMT fp32 strided GEMM: C[m,n] = epi( sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + bias[n] ).
@@ -72,6 +73,8 @@ int ds_conv_wgrad_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, in
                        int kh, int kw, int pad_t, int pad_l, const float* dz, int64_t lddz, int64_t n,
                        float* dw, int64_t lddw, int flags, void* stream);
 
+/* dst[r, 0:cols] = src[r, 0:cols] for `rows` rows (cudaMemcpy2DAsync; concat / split plumbing) */
+int ds_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream);
 /* out[c, r] = in[r, c] */
 int ds_transpose(const float* in, int64_t ldin, int64_t rows, int64_t cols, float* out, int64_t ldout, void* stream);
 /* HWIO [kh,kw,cin,cout] -> forward operand [cout][kh][kw][cin] and input-gradient operand
@@ -83,22 +86,27 @@ int ds_repack_conv_weights(const float* hwio, int kh, int kw, int64_t cin, int64
 /* ---- batch norm (slim.batch_norm center=True scale=False; slim/nets/inception_utils.py:48-70) */
 /* stats[0:N] += column sums of z, stats[N:2N] += column sums of z^2 (double accumulators) */
 int ds_colstats(const float* z, int64_t ldz, int64_t m, int64_t n, double* stats, void* stream);
-/* training: mean/var from stats (biased), y = relu((z-mean)*rsqrt(var+eps)+beta); writes mean/rstd
- * for the backward pass and applies moving <- moving - momentum*(moving - batch).
- * inference (stats == NULL): uses moving_mean / moving_var.   flags: DS_BN_TF32 rounds y to TF32,
- * DS_BN_UNBIASED feeds the unbiased variance to the moving average, DS_BN_NO_RELU skips the ReLU */
+/* one thread per channel: mean/var from stats (biased), mean_out/rstd_out for apply + backward, and the
+ * UPDATE_OPS moving <- moving - momentum*(moving - batch) (moving_* may be NULL).
+ * flags: DS_BN_UNBIASED feeds the unbiased variance to the moving average (fused-BN TF builds) */
 #define DS_BN_TF32 1
 #define DS_BN_UNBIASED 2
 #define DS_BN_NO_RELU 4
-int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const double* stats,
-                     const float* beta, float* moving_mean, float* moving_var, float momentum, float eps,
-                     float* mean_out, float* rstd_out, float* y, int64_t ldy, int flags, void* stream);
-/* backward of relu(bn(z)): g = dy*[bn(z)>0]; sums[0:N] += sum g, sums[N:2N] += sum g*xhat */
+#define DS_BN_USE_VAR 8
+int ds_bn_finalize(const double* stats, int64_t m, int64_t n, float* moving_mean, float* moving_var, float momentum,
+                   float eps, float* mean_out, float* rstd_out, int flags, void* stream);
+/* y = relu((z-mean)*rstd+beta).  DS_BN_USE_VAR: `rstd` holds a variance (inference on moving statistics,
+ * rsqrt(var+eps) applied here); DS_BN_TF32 rounds y to TF32 (it feeds the next tensor-core contraction);
+ * DS_BN_NO_RELU skips the ReLU.  z and y may be column windows of wider buffers (ldz / ldy). */
+int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean, const float* rstd,
+                     float eps, const float* beta, float* y, int64_t ldy, int flags, void* stream);
+/* backward of relu(bn(z)): g = dy*[bn(z)>0]; sums[c] += sum g, sums[sums_ld + c] += sum g*xhat */
 int ds_bn_relu_bwd_reduce(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
-                          const float* mean, const float* rstd, const float* beta, double* sums, void* stream);
+                          const float* mean, const float* rstd, const float* beta, double* sums, int64_t sums_ld,
+                          void* stream);
 /* dz = rstd*(g - sum(g)/m - xhat*sum(g*xhat)/m) written over z; dbeta[n] = sum g; DS_BN_TF32 rounds dz */
 int ds_bn_relu_bwd_apply(const float* dy, int64_t lddy, float* z, int64_t ldz, int64_t m, int64_t n,
-                         const float* mean, const float* rstd, const float* beta, const double* sums,
+                         const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                          float* dbeta, int flags, void* stream);
 
 /* ---- pooling (slim.max_pool2d / avg_pool2d / dropout, image_model/inception_v1.py:67,79,94,118,208,299-302) */

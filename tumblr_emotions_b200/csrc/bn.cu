@@ -75,8 +75,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t M, 
 // y = relu((z - mean) * rstd + beta); `use_var`: rstd argument holds a variance (inference with moving stats)
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                       int use_var, float eps, const float* __restrict__ beta,
+                                                       float eps, const float* __restrict__ beta,
                                                        float* __restrict__ y, int64_t ldy, int flags) {
+  const bool use_var = (flags & DS_BN_USE_VAR) != 0;
   const int64_t ncg = N >> 2;
   const int64_t total = M * ncg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t lddy,
                                                             const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const float* __restrict__ beta, double* __restrict__ sums) {
+                                                            const float* __restrict__ beta, double* __restrict__ sums, int64_t sums_ld) {
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * RED_ROWS;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       atomicAdd(sums + col + i, a[i]);
-      atomicAdd(sums + N + col + i, b[i]);
+      atomicAdd(sums + sums_ld + col + i, b[i]);
     }
   }
 }
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t lddy, float* z, int64_t ldz,
                                                            int64_t M, int64_t N, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ beta,
-                                                           const double* __restrict__ sums, float* dbeta, int flags) {
+                                                           const double* __restrict__ sums, int64_t sums_ld, float* dbeta, int flags) {
   const int64_t ncg = N >> 2;
   const int64_t total = M * ncg;
   const double inv_m = 1.0 / (double)M;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       const float mu = __ldg(mean + col + j), rs = __ldg(rstd + col + j);
       const float xh = (zz[j] - mu) * rs;
       const float g = (xh + __ldg(beta + col + j) > 0.f) ? gg[j] : 0.f;
-      const float m1 = (float)(sums[col + j] * inv_m), m2 = (float)(sums[N + col + j] * inv_m);
+      const float m1 = (float)(sums[col + j] * inv_m), m2 = (float)(sums[sums_ld + col + j] * inv_m);
       out[j] = rs * (g - m1 - xh * m2);
       if (flags & DS_BN_TF32) out[j] = ds::to_tf32(out[j]);
     }
@@ -197,44 +198,45 @@ int ds_colstats(const float* z, int64_t ldz, int64_t m, int64_t n, double* stats
   return 0;
 }
 
-int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const double* stats, const float* beta,
-                     float* moving_mean, float* moving_var, float momentum, float eps, float* mean_out, float* rstd_out,
-                     float* y, int64_t ldy, int flags, void* stream) {
-  DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
-  DS_REQUIRE(stats || (moving_mean && moving_var), "inference mode needs moving statistics");
+int ds_bn_finalize(const double* stats, int64_t m, int64_t n, float* moving_mean, float* moving_var, float momentum, float eps,
+                   float* mean_out, float* rstd_out, int flags, void* stream) {
+  DS_REQUIRE(stats && mean_out && rstd_out, "ds_bn_finalize needs stats, mean_out and rstd_out");
+  DS_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "moving_mean / moving_var go together");
   if (m == 0 || n == 0) return 0;
-  if (stats) {
-    DS_REQUIRE(mean_out && rstd_out, "training mode needs mean_out / rstd_out");
-    bn_finalize_kernel<<<(unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream)>>>(stats, m, n, moving_mean, moving_var, momentum, eps,
-                                                                             mean_out, rstd_out, flags);
-    DS_LAUNCH_CHECK();
-    bn_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(z, ldz, m, n, mean_out, rstd_out, 0, eps, beta, y, ldy,
-                                                                             flags);
-  } else {
-    bn_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(z, ldz, m, n, moving_mean, moving_var, 1, eps, beta, y,
-                                                                             ldy, flags);
-  }
+  bn_finalize_kernel<<<(unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream)>>>(stats, m, n, moving_mean, moving_var, momentum, eps, mean_out,
+                                                                           rstd_out, flags);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean, const float* rstd, float eps,
+                     const float* beta, float* y, int64_t ldy, int flags, void* stream) {
+  DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
+  DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)y) & 15) == 0, "16-byte alignment");
+  if (m == 0 || n == 0) return 0;
+  bn_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y, ldy, flags);
   DS_LAUNCH_CHECK();
   return 0;
 }
 
 int ds_bn_relu_bwd_reduce(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
-                          const float* mean, const float* rstd, const float* beta, double* sums, void* stream) {
+                          const float* mean, const float* rstd, const float* beta, double* sums, int64_t sums_ld, void* stream) {
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
   const dim3 blk = red_block(n);
   dim3 grid((unsigned)ds::cdiv(n / 4, blk.x), (unsigned)ds::cdiv(m, RED_ROWS));
-  bn_bwd_reduce_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums);
+  bn_bwd_reduce_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld);
   DS_LAUNCH_CHECK();
   return 0;
 }
 
 int ds_bn_relu_bwd_apply(const float* dy, int64_t lddy, float* z, int64_t ldz, int64_t m, int64_t n, const float* mean,
-                         const float* rstd, const float* beta, const double* sums, float* dbeta, int flags, void* stream) {
+                         const float* rstd, const float* beta, const double* sums, int64_t sums_ld, float* dbeta, int flags,
+                         void* stream) {
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
   bn_bwd_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums,
-                                                                               dbeta, flags);
+                                                                               sums_ld, dbeta, flags);
   DS_LAUNCH_CHECK();
   return 0;
 }

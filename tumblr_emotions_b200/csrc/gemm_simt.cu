@@ -181,11 +181,11 @@ int ds_gemm_simt(const float* a, int64_t sam, int64_t sak, const float* b, int64
 }
 
 int ds_conv_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
-                 int pad_t, int pad_l, int64_t ho, int64_t wo, const float* w_kn, int64_t ldw, int64_t n, float* y,
+                 int pad_t, int pad_l, int64_t ho, int64_t wo, const float* wgt, int64_t swk, int64_t swn, int64_t n, float* y,
                  int64_t ldy, const float* bias, int flags, void* stream) {
   const int64_t M = batch * ho * wo, K = (int64_t)kh * kw * cin;
   ALoadConv A{x, ldx, M, K, (int)h, (int)w, (int)cin, kw, stride, pad_t, pad_l, (int)ho, (int)wo};
-  return launch(A, true, w_kn, ldw, 1, y, ldy, M, n, K, bias, flags, 1, ds::S(stream));
+  return launch(A, true, wgt, swk, swn, y, ldy, M, n, K, bias, flags, 1, ds::S(stream));
 }
 
 int ds_conv_wgrad_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw,
@@ -194,6 +194,13 @@ int ds_conv_wgrad_simt(const float* x, int64_t ldx, int64_t batch, int64_t h, in
   const int64_t M = (int64_t)kh * kw * cin, K = batch * h * w;
   ALoadConvT A{x, ldx, M, K, (int)h, (int)w, (int)cin, kw, pad_t, pad_l};
   return launch(A, false, dz, lddz, 1, dw, lddw, M, n, K, nullptr, flags, pick_splits(M, n, K), ds::S(stream));
+}
+
+int ds_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  DS_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), cols * sizeof(float), rows,
+                            cudaMemcpyDeviceToDevice, ds::S(stream)));
+  return 0;
 }
 
 int ds_transpose(const float* in, int64_t ldin, int64_t rows, int64_t cols, float* out, int64_t ldout, void* stream) {

@@ -11,7 +11,7 @@ import torch
 from ._lib import lib
 
 EPI_RELU, EPI_ACCUMULATE, EPI_STATS = 1, 2, 4
-BN_TF32, BN_UNBIASED, BN_NO_RELU = 1, 2, 4
+BN_TF32, BN_UNBIASED, BN_NO_RELU, BN_USE_VAR = 1, 2, 4, 8
 
 
 def _stream() -> int:
@@ -66,9 +66,10 @@ def gemm_tc(a: View, bt, ldb, n, c: View, k=None, bias=None, flags=0):
     conv_tc(a, a.rows, 1, 1, k if k is not None else a.cols, 1, bt, ldb, n, c, None, bias, None, flags)
 
 
-def conv_simt(x: View, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, w_kn, n, y: View, bias=None, flags=0):
-    lib().conv_simt(x.ptr, x.ld, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, _p(w_kn), n, n, y.ptr, y.ld,
-                    _p(bias), flags, _stream())
+def conv_simt(x: View, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, wgt, n, y: View, bias=None, flags=0,
+              swk=None, swn=1):
+    lib().conv_simt(x.ptr, x.ld, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, _p(wgt), swk if swk is not None else n,
+                    swn, n, y.ptr, y.ld, _p(bias), flags, _stream())
 
 
 def gemm_simt(a_ptr, sam, sak, b_ptr, sbk, sbn, c: View, m, n, k, bias=None, flags=0):
@@ -95,6 +96,10 @@ def conv_wgrad_simt(x: View, batch, h, w, cin, kh, kw, pad_t, pad_l, dz: View, n
                           _stream())
 
 
+def copy2d(src: View, dst: View):
+    lib().copy2d(src.ptr, src.ld, dst.ptr, dst.ld, src.rows, src.cols, _stream())
+
+
 def transpose(src: View, dst: View):
     lib().transpose(src.ptr, src.ld, src.rows, src.cols, dst.ptr, dst.ld, _stream())
 
@@ -110,18 +115,22 @@ def colstats(z: View, stats):
     lib().colstats(z.ptr, z.ld, z.rows, z.cols, _p(stats), _stream())
 
 
-def bn_apply_relu(z: View, stats, beta, moving_mean, moving_var, momentum, eps, mean_out, rstd_out, y: View, flags=0):
-    lib().bn_apply_relu(z.ptr, z.ld, z.rows, z.cols, _p(stats), _p(beta), _p(moving_mean), _p(moving_var), momentum, eps,
-                        _p(mean_out), _p(rstd_out), y.ptr, y.ld, flags, _stream())
+def bn_finalize(stats, m, n, moving_mean, moving_var, momentum, eps, mean_out, rstd_out, flags=0):
+    lib().bn_finalize(_p(stats), m, n, _p(moving_mean), _p(moving_var), momentum, eps, _p(mean_out), _p(rstd_out), flags, _stream())
 
 
-def bn_relu_bwd_reduce(dy: View, z: View, mean, rstd, beta, sums):
-    lib().bn_relu_bwd_reduce(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), _stream())
+def bn_apply_relu(z: View, mean, rstd, eps, beta, y: View, flags=0):
+    lib().bn_apply_relu(z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), eps, _p(beta), y.ptr, y.ld, flags, _stream())
 
 
-def bn_relu_bwd_apply(dy: View, z: View, mean, rstd, beta, sums, dbeta, flags=0):
-    lib().bn_relu_bwd_apply(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), _p(dbeta),
-                            flags, _stream())
+def bn_relu_bwd_reduce(dy: View, z: View, mean, rstd, beta, sums, sums_ld):
+    lib().bn_relu_bwd_reduce(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
+                             _stream())
+
+
+def bn_relu_bwd_apply(dy: View, z: View, mean, rstd, beta, sums, sums_ld, dbeta, flags=0):
+    lib().bn_relu_bwd_apply(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
+                            _p(dbeta), flags, _stream())
 
 
 # ---- pooling -------------------------------------------------------------------------------------
