@@ -154,6 +154,9 @@ int ds_relu_bwd(float* dy, const float* y, int64_t n, void* stream);
 int ds_round_tf32(float* x, int64_t n, void* stream);
 /* tf.train.AdamOptimizer (im_text_rnn_model.py:134): hyper (device) = {lr_t, beta1, beta2, eps, grad_scale};
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps), lr_t pre-corrected by the host */
+/* hyper[0:5] = {lr_t, beta1, beta2, eps, grad_scale}, written by a 1-thread kernel (values travel as launch
+ * arguments, so the update is stream-ordered with the graph replay that consumes it) */
+int ds_fill_hyper(float* hyper, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
 int ds_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream);
 
 #ifdef __cplusplus

@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+__global__ void fill_hyper_kernel(float* h, float a, float b, float c, float d, float e) {
+  h[0] = a; h[1] = b; h[2] = c; h[3] = d; h[4] = e;
+}
+
 int blocks_for(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(ds::cdiv(total, 256), 148 * 8)); }
 
 }  // namespace
@@ -173,6 +177,12 @@ int ds_relu_bwd(float* dy, const float* y, int64_t n, void* stream) {
 int ds_round_tf32(float* x, int64_t n, void* stream) {
   if (n == 0) return 0;
   round_tf32_kernel<<<blocks_for(n), 256, 0, ds::S(stream)>>>(x, n);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_fill_hyper(float* hyper, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  fill_hyper_kernel<<<1, 1, 0, ds::S(stream)>>>(hyper, lr_t, beta1, beta2, eps, grad_scale);
   DS_LAUNCH_CHECK();
   return 0;
 }

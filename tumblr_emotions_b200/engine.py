@@ -1,0 +1,672 @@
+"""Host-side schedule of the Deep Sentiment step on one B200: static buffers + the ordered kernel launches.
+
+The engine mirrors what one `session.run(train_op)` does in the reference
+(image_text_model/im_text_rnn_model.py:107-169; image_model/im_model.py:166-225; text_model/text_embedding.py:89-150):
+forward of the Inception-v1 tower (image_model/inception_v1.py) and the embedding+LSTM tower, concat/FC/softmax
+head, softmax-xent + L2 loss, gradients w.r.t. the reference's trainable set (every BN beta, Mixed_5c + Logits
+weights, LSTM, FC - SURVEY F6), BN moving-average updates and TF-Adam.  All arithmetic runs in libdeepsent.so
+kernels; torch only owns the device memory, the streams and (for N>1) the NCCL all-reduce.
+
+Data layout in HBM (per GPU, batch B):
+  activations   NHWC fp32; every conv "unit" keeps its raw output Z [B*H*W, N] (needed by BN backward, overwritten in
+                place by dZ) and writes relu(bn(Z)) straight into the channel slice of its consumer's buffer (the
+                inception block's concat output OUT, or the reduce buffer T shared by the two 3x3 branches).
+  weights       masters in TF layout (HWIO / [in,out]) inside one flat trainable arena (params | grads | adam m | v
+                share the layout so Adam and the all-reduce are single flat launches); tensor-core operand copies
+                (K-major, TF32-rounded; forward [Cout][r][s][Cin] and input-gradient [Cin][r'][s'][Cout]) are rebuilt
+                after each update for trainable layers, once for frozen ones.
+  BN            beta / moving stats / batch mean, rstd / fp64 sum accumulators live in arenas ordered by unit so the
+                sibling 1x1 convs of a block (one fused GEMM) see contiguous slices.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import View
+from .topology import (BN_DECAY, BN_EPS, DROPOUT_KEEP, ENDPOINTS, FORGET_BIAS, IMAGE_SIZE, MIXED, SEQUENCE,
+                       TRAINABLE_WEIGHT_PREFIXES, WEIGHT_DECAY, mixed_convs, same_pad)
+
+EMB_LD = 64      # embedding rows padded 50 -> 64 floats so every row is 16-byte aligned
+
+
+def _align4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# conv + batch-norm unit
+# ----------------------------------------------------------------------------------------------------------------
+class ConvUnit:
+    """One contraction + train-mode BN + ReLU.  `scopes` has >1 entry for the fused sibling 1x1 convs of an inception
+    block (same input -> one GEMM with concatenated output channels)."""
+
+    def __init__(self, eng: "Engine", scopes: List[str], k: int, stride: int, cin: int, couts: List[int], h_in: int,
+                 x: View, outs: List[View], dx: Optional[View], douts: List[View], seg_cols: List[Tuple[int, int]],
+                 dx_accumulate: bool = False):
+        self.eng, self.scopes, self.k, self.stride, self.cin, self.couts, self.h_in = eng, scopes, k, stride, cin, couts, h_in
+        self.h_out, self.pad, _ = same_pad(h_in, k, stride)
+        self.N = sum(couts)
+        self.M = eng.batch * self.h_out * self.h_out
+        self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
+        self.tc = eng.precision == "tf32" and stride == 1 and k in (1, 3) and cin % 8 == 0
+        self.Z = eng.new(self.M, self.N)
+        off = eng.bn_cursor
+        eng.bn_cursor += self.N
+        self.bn_off = off
+        self.scope_cols = []
+        c = 0
+        for s, n in zip(scopes, couts):
+            self.scope_cols.append((s, c, n))
+            eng.bn_index[s] = (off + c, n)
+            c += n
+        self.trainable = scopes[0].startswith(TRAINABLE_WEIGHT_PREFIXES)
+        kk = k * k
+        self.w_fwd = eng.new(self.N, kk * cin) if self.tc else None          # [N][r][s][cin]
+        self.w_dgrad = eng.new(cin, kk * self.N)                              # [cin][r'][s'][N]
+
+    # -- operand copies ------------------------------------------------------------------------------------
+    def refresh_operands(self):
+        e = self.eng
+        kk = self.k * self.k
+        for s, c, n in self.scope_cols:
+            w = e.weight(s + "/weights")
+            fwd = self.w_fwd[c:c + n] if self.tc else None
+            ops.repack_conv_weights(w, fwd=fwd, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
+                                    round_tf32=self.tc)
+
+    def bind(self):
+        e = self.eng
+        o, n = self.bn_off, self.N
+        self.beta, self.dbeta = e.beta[o:o + n], e.dbeta[o:o + n]
+        self.mov_mean, self.mov_var = e.moving_mean[o:o + n], e.moving_var[o:o + n]
+        self.mean, self.rstd = e.bn_mean[o:o + n], e.bn_rstd[o:o + n]
+        self.stats, self.sums = e.stats[2 * o:2 * o + 2 * n], e.sums[2 * o:2 * o + 2 * n]
+
+    # -- forward -------------------------------------------------------------------------------------------
+    def fwd(self, train: bool):
+        e, B, h = self.eng, self.eng.batch, self.h_in
+        Zv = View(self.Z)
+        if self.tc:
+            ops.conv_tc(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.k * self.k * self.cin, self.N, Zv,
+                        stats=self.stats if train else None)
+        else:
+            if len(self.scopes) == 1:
+                ops.conv_simt(self.x, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
+                              e.weight(self.scopes[0] + "/weights"), self.N, Zv)
+            else:   # fused 1x1 siblings: the input-gradient operand [cin][N] *is* the concatenated HWIO matrix
+                ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
+            if train:
+                ops.colstats(Zv, self.stats)
+        flags = ops.BN_TF32 if e.precision == "tf32" else 0
+        if train:
+            ops.bn_finalize(self.stats, self.M, self.N, self.mov_mean, self.mov_var, 1.0 - BN_DECAY, BN_EPS, self.mean, self.rstd,
+                            ops.BN_UNBIASED if e.unbiased_moving_var else 0)
+            for (c, n), out in zip(self.segs, self.outs):
+                ops.bn_apply_relu(Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], BN_EPS, self.beta[c:c + n], out, flags)
+        else:
+            for (c, n), out in zip(self.segs, self.outs):
+                ops.bn_apply_relu(Zv.slice(c, n), self.mov_mean[c:c + n], self.mov_var[c:c + n], BN_EPS, self.beta[c:c + n], out,
+                                  flags | ops.BN_USE_VAR)
+
+    # -- backward ------------------------------------------------------------------------------------------
+    def bwd(self):
+        e, B, h = self.eng, self.eng.batch, self.h_out
+        Zv = View(self.Z)
+        for (c, n), dy in zip(self.segs, self.douts):
+            ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
+                                   self.N)
+        flags = ops.BN_TF32 if (e.precision == "tf32" and self.dx is not None) else 0
+        for (c, n), dy in zip(self.segs, self.douts):
+            ops.bn_relu_bwd_apply(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
+                                  self.N, self.dbeta[c:c + n], flags)
+        if self.trainable:   # Conv2DBackpropFilter only where the reference trains weights (inception_v1.py:229-235)
+            for s, c, n in self.scope_cols:
+                ops.conv_wgrad_simt(self.x, B, self.h_in, self.h_in, self.cin, self.k, self.k, self.pad, self.pad, Zv.slice(c, n), n,
+                                    e.grad(s + "/weights"))
+        if self.dx is not None:
+            fl = ops.EPI_ACCUMULATE if self.dx_accumulate else 0
+            if self.tc:
+                ops.conv_tc(Zv, B, h, h, self.N, self.k, self.w_dgrad, self.k * self.k * self.N, self.cin, self.dx, flags=fl)
+            else:
+                ops.conv_simt(Zv, B, h, h, self.N, self.k, self.k, 1, self.pad, self.pad, h, h, self.w_dgrad, self.cin, self.dx,
+                              flags=fl, swk=1, swn=self.k * self.k * self.N)
+
+
+class PoolNode:
+    def __init__(self, eng, k, stride, c, h_in, x: View, y: View, dx: View, dy: View, dx_accumulate=False):
+        self.eng, self.k, self.stride, self.c, self.h_in = eng, k, stride, c, h_in
+        self.h_out, self.pad, _ = same_pad(h_in, k, stride)
+        self.x, self.y, self.dx, self.dy, self.dx_accumulate = x, y, dx, dy, dx_accumulate
+        self.argmax = torch.empty(eng.batch * self.h_out * self.h_out * c, dtype=torch.uint8, device=eng.device)
+
+    def fwd(self, train):
+        B = self.eng.batch
+        ops.maxpool_fwd(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
+                        self.y, self.argmax if train else None)
+
+    def bwd(self):
+        B = self.eng.batch
+        ops.maxpool_bwd(self.dy, self.argmax, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
+                        self.h_out, self.dx, self.dx_accumulate)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# engine
+# ----------------------------------------------------------------------------------------------------------------
+class Engine:
+    """model in {'joint', 'image', 'text'} (DeepSentiment / ImageModel / TextModel of the reference)."""
+
+    def __init__(self, model: str = "joint", batch: int = 64, nb_emotions: int = 15, im_features: int = 256,
+                 rnn_size: int = 1024, fc_size: int = 512, vocab: int = 400001, emb_dim: int = 50, post_size: int = 50,
+                 precision: str = "tf32", device: int = 0, seed: int = 0, world_size: int = 1, dropout: str = "rng",
+                 unbiased_moving_var: bool = False, final_endpoint: str = "Mixed_5c", training: bool = True):
+        if model not in ("joint", "image", "text"):
+            raise ValueError("unknown model %r" % model)
+        if precision not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' (tcgen05) or 'fp32' (SIMT cross-check)")
+        if final_endpoint not in ENDPOINTS:
+            raise ValueError("Unknown final endpoint %s" % final_endpoint)      # image_model/inception_v1.py:251
+        if final_endpoint != "Mixed_5c":
+            raise NotImplementedError("only the reference's configured final_endpoint 'Mixed_5c' is built")
+        if not torch.cuda.is_available():
+            raise RuntimeError("tumblr_emotions_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.model, self.batch, self.nb_emotions, self.im_features = model, batch, nb_emotions, im_features
+        self.rnn_size, self.fc_size, self.vocab, self.emb_dim, self.post_size = rnn_size, fc_size, vocab, emb_dim, post_size
+        self.precision, self.world_size, self.dropout, self.unbiased_moving_var = precision, world_size, dropout, unbiased_moving_var
+        self.training = training
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        ops.init(device)
+        self.seed = seed
+        self.has_image, self.has_text = model in ("joint", "image"), model in ("joint", "text")
+        self.tower_classes = im_features if model == "joint" else nb_emotions
+        self.bn_cursor, self.bn_index = 0, {}
+        self.nodes, self.units = [], []
+        self.adam_t = 0
+        self._graph = None
+        self._bytes = 0
+
+        B = batch
+        # ---- static input buffers ----
+        if self.has_image:
+            self.images = self.new(B, IMAGE_SIZE, IMAGE_SIZE, 3)
+        if self.has_text:
+            self.ids = torch.zeros(B, post_size, dtype=torch.int64, device=self.device)
+            self.seq_lens = torch.ones(B, dtype=torch.int64, device=self.device)
+        self.labels = torch.zeros(B, dtype=torch.int64, device=self.device)
+
+        # ---- graph construction (allocates activations / gradients, records the parameter table) ----
+        if self.has_image:
+            self._build_tower()
+        self._layout_params()
+        for u in self.units:
+            u.bind()
+        if self.has_text:
+            self._build_text()
+        self._build_head()
+        self.init_params(seed)
+
+    # -- memory ------------------------------------------------------------------------------------------------
+    def new(self, *shape, dtype=torch.float32, zero=True):
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self._bytes += t.numel() * t.element_size()
+        return t
+
+    # -- tower construction -----------------------------------------------------------------------------------
+    def _build_tower(self):
+        B, tr = self.batch, self.training
+        act = View(self.images)
+        dact = None                      # no gradient w.r.t. the images
+        c, h = 3, IMAGE_SIZE
+        for item in SEQUENCE:
+            kind, name = item[0], item[1]
+            if kind == "conv":
+                _, _, k, s, cout = item
+                ho = same_pad(h, k, s)[0]
+                out = self.new(B, ho, ho, cout)
+                dout = self.new(B, ho, ho, cout) if tr else None
+                u = ConvUnit(self, ["InceptionV1/" + name], k, s, c, [cout], h, act, [View(out)], dact,
+                             [View(dout)] if tr else [None], [(0, cout)])
+                self.units.append(u); self.nodes.append(u)
+                act, dact, c, h = View(out), View(dout) if tr else None, cout, ho
+            elif kind == "maxpool":
+                _, _, k, s = item
+                ho = same_pad(h, k, s)[0]
+                out = self.new(B, ho, ho, c)
+                dout = self.new(B, ho, ho, c) if tr else None
+                self.nodes.append(PoolNode(self, k, s, c, h, act, View(out), dact, View(dout) if tr else None))
+                act, dact, h = View(out), View(dout) if tr else None, ho
+            else:
+                c0, c1a, c1b, c2a, c2b, c3, _ = MIXED[name]
+                convs = mixed_convs(name, c)
+                ctot = c0 + c1b + c2b + c3
+                OUT, T, P = self.new(B, h, h, ctot), self.new(B, h, h, c1a + c2a), self.new(B, h, h, c)
+                dOUT = self.new(B, h, h, ctot) if tr else None
+                dT = self.new(B, h, h, c1a + c2a) if tr else None
+                dP = self.new(B, h, h, c) if tr else None
+                vO, vT, vP = View(OUT), View(T), View(P)
+                g = (lambda t, *a: View(t).slice(*a) if a else View(t)) if tr else (lambda t, *a: None)
+                # fused sibling 1x1s (Branch_0, Branch_1 reduce, Branch_2 reduce) - inception_v1.py:85-91 pattern
+                u1 = ConvUnit(self, [convs[0][0], convs[1][0], convs[3][0]], 1, 1, c, [c0, c1a, c2a], h, act,
+                              [vO.slice(0, c0), vT], dact, [g(dOUT, 0, c0), g(dT)], [(0, c0), (c0, c1a + c2a)])
+                u2 = ConvUnit(self, [convs[2][0]], 3, 1, c1a, [c1b], h, vT.slice(0, c1a), [vO.slice(c0, c1b)], g(dT, 0, c1a),
+                              [g(dOUT, c0, c1b)], [(0, c1b)])
+                u3 = ConvUnit(self, [convs[4][0]], 3, 1, c2a, [c2b], h, vT.slice(c1a, c2a), [vO.slice(c0 + c1b, c2b)],
+                              g(dT, c1a, c2a), [g(dOUT, c0 + c1b, c2b)], [(0, c2b)])
+                pool = PoolNode(self, 3, 1, c, h, act, vP, dact, g(dP), dx_accumulate=True)
+                u4 = ConvUnit(self, [convs[5][0]], 1, 1, c, [c3], h, vP, [vO.slice(c0 + c1b + c2b, c3)], g(dP),
+                              [g(dOUT, c0 + c1b + c2b, c3)], [(0, c3)])
+                self.units += [u1, u2, u3, u4]
+                # forward order; backward runs the reversed list, so the fused unit's input gradient (overwrite)
+                # must come *before* the pool's accumulate in reverse order -> pool is listed before u1
+                self.nodes += [pool, u1, u2, u3, u4]
+                act, dact, c = vO, View(dOUT) if tr else None, ctot
+        self.tower_out, self.d_tower_out, self.tower_c, self.tower_h = act, dact, c, h
+        self.feat = self.new(B, c)
+        self.dfeat = self.new(B, c) if tr else None
+        self.drop_mask = self.new(B, c) if self.dropout != "none" else None
+        self.drop_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    # -- parameters -------------------------------------------------------------------------------------------
+    def _layout_params(self):
+        """Flat trainable arena: [L2-regularised conv weights | Logits bias | all BN betas (unit order) | LSTM | FC]."""
+        tbl: List[Tuple[str, Tuple[int, ...]]] = []
+        self.frozen_shapes: Dict[str, Tuple[int, ...]] = {}
+        if self.has_image:
+            for u in self.units:
+                for s, c, n in u.scope_cols:
+                    shp = (u.k, u.k, u.cin, n)
+                    if u.trainable:
+                        tbl.append((s + "/weights", shp))
+                    else:
+                        self.frozen_shapes[s + "/weights"] = shp
+            tbl.append(("InceptionV1/Logits/Conv2d_0c_1x1/weights", (1, 1, self.tower_c, self.tower_classes)))
+        self.l2_names = [n for n, _ in tbl]
+        if self.has_image:
+            tbl.append(("InceptionV1/Logits/Conv2d_0c_1x1/biases", (self.tower_classes,)))
+            self.n_bn = self.bn_cursor
+            tbl.append(("__betas__", (self.n_bn,)))
+        if self.has_text:
+            self.frozen_shapes["Text/W_embedding"] = (self.vocab, self.emb_dim)
+            tbl.append(("Text/rnn/basic_lstm_cell/kernel", (self.emb_dim + self.rnn_size, 4 * self.rnn_size)))
+            tbl.append(("Text/rnn/basic_lstm_cell/bias", (4 * self.rnn_size,)))
+        if self.model == "joint":
+            tbl += [("W_fc", (self.im_features + self.rnn_size, self.fc_size)), ("b_fc", (self.fc_size,)),
+                    ("W_softmax", (self.fc_size, self.nb_emotions)), ("b_softmax", (self.nb_emotions,))]
+        elif self.model == "text":
+            tbl += [("W_softmax", (self.rnn_size, self.nb_emotions)), ("b_softmax", (self.nb_emotions,))]
+        off, self.slots, self.l2_len = 0, {}, 0
+        for i, (name, shp) in enumerate(tbl):
+            n = int(math.prod(shp))
+            self.slots[name] = (off, n, shp)
+            off = _align4(off + n)
+            if i == len(self.l2_names) - 1:
+                self.l2_len = off            # the L2-regularised conv weights form the arena prefix [0, l2_len)
+        self.n_params = off
+        self.params, self.grads = self.new(off), self.new(off)
+        self.adam_m, self.adam_v = self.new(off), self.new(off)
+        self.hyper = self.new(8)
+        self.frozen = {k: self.new(*shp) for k, shp in self.frozen_shapes.items()}
+        if self.has_image:
+            o, n, _ = self.slots["__betas__"]
+            self.beta, self.dbeta = self.params[o:o + n], self.grads[o:o + n]
+            self.moving_mean, self.moving_var = self.new(n), self.new(n)
+            self.moving_var.fill_(1.0)
+            self.bn_mean, self.bn_rstd = self.new(n), self.new(n)
+            self.stats, self.sums = self.new(2 * n, dtype=torch.float64), self.new(2 * n, dtype=torch.float64)
+        self.loss_buf = self.new(4)          # [total, xent, l2_trainable, l2_frozen_const]
+
+    def _slot(self, arena, name):
+        o, n, shp = self.slots[name]
+        return arena[o:o + n].view(shp)
+
+    def weight(self, name) -> torch.Tensor:
+        return self._slot(self.params, name) if name in self.slots else self.frozen[name]
+
+    def grad(self, name) -> torch.Tensor:
+        return self._slot(self.grads, name)
+
+    def trainable_names(self) -> List[str]:
+        out = []
+        for name in self.slots:
+            if name == "__betas__":
+                out += [s + "/BatchNorm/beta" for u in self.units for s, _, _ in u.scope_cols]
+            else:
+                out.append(name)
+        return out
+
+    def n_trainable(self) -> int:
+        return sum(int(math.prod(self.tensor(n).shape)) for n in self.trainable_names())
+
+    def tensor(self, name: str, arena: str = "params") -> torch.Tensor:
+        """Device view of a variable by its TensorFlow name (reference checkpoint naming)."""
+        src = {"params": self.params, "grads": self.grads, "m": self.adam_m, "v": self.adam_v}[arena]
+        if name.endswith("/BatchNorm/beta"):
+            o, n = self.bn_index[name[:-len("/BatchNorm/beta")]]
+            base = self.slots["__betas__"][0]
+            return src[base + o:base + o + n]
+        if name.endswith("/BatchNorm/moving_mean"):
+            o, n = self.bn_index[name[:-len("/BatchNorm/moving_mean")]]
+            return self.moving_mean[o:o + n]
+        if name.endswith("/BatchNorm/moving_variance"):
+            o, n = self.bn_index[name[:-len("/BatchNorm/moving_variance")]]
+            return self.moving_var[o:o + n]
+        if name in self.slots:
+            return self._slot(src, name)
+        if arena != "params":
+            raise KeyError("%s is not trainable" % name)
+        return self.frozen[name]
+
+    def variable_names(self) -> List[str]:
+        names = []
+        if self.has_image:
+            for u in self.units:
+                for s, _, _ in u.scope_cols:
+                    names += [s + "/weights", s + "/BatchNorm/beta", s + "/BatchNorm/moving_mean", s + "/BatchNorm/moving_variance"]
+            names += ["InceptionV1/Logits/Conv2d_0c_1x1/weights", "InceptionV1/Logits/Conv2d_0c_1x1/biases"]
+        if self.has_text:
+            names += ["Text/W_embedding", "Text/rnn/basic_lstm_cell/kernel", "Text/rnn/basic_lstm_cell/bias"]
+        if self.model == "joint":
+            names += ["W_fc", "b_fc", "W_softmax", "b_softmax"]
+        elif self.model == "text":
+            names += ["W_softmax", "b_softmax"]
+        return names
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: self.tensor(n).detach().cpu().clone() for n in self.variable_names()}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True, exclude_prefixes: Tuple[str, ...] = ()):
+        for n in self.variable_names():
+            if n.startswith(tuple(exclude_prefixes)) if exclude_prefixes else False:
+                continue
+            if n not in sd:
+                if strict:
+                    raise KeyError("missing variable %s" % n)
+                continue
+            t = self.tensor(n)
+            src = torch.as_tensor(sd[n], dtype=torch.float32)
+            if tuple(src.shape) != tuple(t.shape):
+                raise ValueError("shape mismatch for %s: %s vs %s" % (n, tuple(src.shape), tuple(t.shape)))
+            t.copy_(src.to(self.device))
+        self.refresh_operands(everything=True)
+
+    def init_params(self, seed: int = 0):
+        """Initialisers of the reference graph: conv trunc_normal(0.01) (inception_v1.py:59), Logits
+        variance_scaling (slim default), beta 0, moving stats 0/1, LSTM + FC glorot_uniform (TF get_variable default,
+        im_text_rnn_model.py:98-104), LSTM bias 0, embedding = stand-in for GloVe with the <ukn> zero row (:75-76)."""
+        g = torch.Generator().manual_seed(seed)
+
+        def trunc(shape, std):
+            t = torch.empty(shape)
+            torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=g)
+            return t
+
+        def glorot(shape):
+            fi, fo = (shape[0], shape[0]) if len(shape) == 1 else (shape[-2], shape[-1])
+            lim = math.sqrt(6.0 / (fi + fo))
+            return (torch.rand(shape, generator=g) * 2 - 1) * lim
+
+        sd = {}
+        for n in self.variable_names():
+            shp = tuple(self.tensor(n).shape)
+            if n.endswith("/moving_variance"):
+                sd[n] = torch.ones(shp)
+            elif n.endswith(("/beta", "/moving_mean", "/biases", "cell/bias")):
+                sd[n] = torch.zeros(shp)
+            elif n.startswith("InceptionV1/Logits"):
+                sd[n] = trunc(shp, math.sqrt(2.0 / self.tower_c) / 0.87962566103423978)
+            elif n.startswith("InceptionV1/"):
+                sd[n] = trunc(shp, 0.01)
+            elif n == "Text/W_embedding":
+                emb = torch.randn(shp, generator=g) * 0.4
+                emb[-1] = 0.0
+                sd[n] = emb
+            else:
+                sd[n] = glorot(shp)
+        self.load_state_dict(sd)
+
+    def refresh_operands(self, everything: bool = False):
+        """Rebuild the kernel-side operand copies from the TF-layout masters (all of them once, then only the
+        trainable ones after each Adam update)."""
+        if self.has_image:
+            for u in self.units:
+                if everything or u.trainable:
+                    u.refresh_operands()
+            if everything:      # constant part of the L2 term: frozen conv weights
+                self.loss_buf[3:4].zero_()
+                for k, t in self.frozen.items():
+                    if k.endswith("/weights"):
+                        ops.sumsq(t, 0.5 * WEIGHT_DECAY, self.loss_buf[3:4], accumulate=True)
+        if self.has_text and self.precision == "tf32":
+            kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
+            wh = kern[self.emb_dim:]
+            ops.transpose(View(wh), View(self.whT))           # [4n, n]: forward operand (K-major)
+            ops.round_tf32(self.whT)
+            self.wh_r.copy_(wh)                               # [n, 4n]: BPTT operand
+            ops.round_tf32(self.wh_r)
+
+    # -- text tower (im_text_rnn_model.py:80-92 / text_embedding.py:72-82) -------------------------------------
+    def _build_text(self):
+        B, T, n, tr = self.batch, self.post_size, self.rnn_size, self.training
+        self.E = self.new(T * B, EMB_LD)
+        self.XW = self.new(T * B, 4 * n)
+        self.H, self.C = self.new(T + 1, B, n), self.new(T + 1, B, n)
+        self.G = self.new(T, B, 4 * n) if tr else self.new(1, B, 4 * n)
+        self.ZH = self.new(B, 4 * n)
+        self.text_feat = View(self.H[T])
+        if self.precision == "tf32":
+            self.whT, self.wh_r = self.new(4 * n, n), self.new(n, 4 * n)
+        if tr:
+            self.DZ = self.new(T * B, 4 * n)
+            self.dh_carry, self.dc, self.dh_rec = self.new(B, n), self.new(B, n), self.new(B, n)
+
+    def text_fwd(self, train: bool):
+        B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
+        tc = self.precision == "tf32"
+        kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
+        bias = self.weight("Text/rnn/basic_lstm_cell/bias")
+        ops.embedding_gather(self.frozen["Text/W_embedding"], self.ids, View(self.E))
+        # input projection for all time steps at once (exact fp32: keeps the gathered rows bit-exact operands)
+        ops.gemm_nn(View(self.E, e), View(kern[:e]), View(self.XW))
+        for t in range(T):
+            if tc:
+                ops.gemm_tc(View(self.H[t]), self.whT, n, 4 * n, View(self.ZH))
+            else:
+                ops.gemm_nn(View(self.H[t]), View(kern[e:]), View(self.ZH))
+            ops.lstm_gates_fwd(self.ZH, self.XW[t * B:(t + 1) * B], bias, self.C[t], self.H[t], self.seq_lens, t, B, n, FORGET_BIAS,
+                               self.G[t if train else 0], self.C[t + 1], self.H[t + 1], tc)
+
+    def text_bwd(self, dlast: View):
+        B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
+        tc = self.precision == "tf32"
+        kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
+        ops.copy2d(dlast, View(self.dh_carry))
+        self.dc.zero_()
+        for t in reversed(range(T)):
+            ops.lstm_gates_bwd(self.G[t], self.C[t], self.C[t + 1], self.seq_lens, t, B, n, self.dh_rec if t < T - 1 else None,
+                               self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], tc)
+            if t > 0:
+                dz = View(self.DZ[t * B:(t + 1) * B])
+                if tc:
+                    ops.gemm_tc(dz, self.wh_r, 4 * n, n, View(self.dh_rec))
+                else:
+                    ops.gemm_nt(dz, View(kern[e:]), View(self.dh_rec))
+        dk = self.grad("Text/rnn/basic_lstm_cell/kernel")
+        ops.gemm_tn(View(self.E, e), View(self.DZ), View(dk[:e]))
+        ops.gemm_tn(View(self.H[:T].view(T * B, n)), View(self.DZ), View(dk[e:]))
+        ops.colsum(View(self.DZ), self.grad("Text/rnn/basic_lstm_cell/bias"))
+
+    # -- head ------------------------------------------------------------------------------------------------
+    def _build_head(self):
+        B, tr = self.batch, self.training
+        ncls_ld = _align4(self.nb_emotions)
+        self.logits = self.new(B, ncls_ld)
+        self.dlogits = self.new(B, ncls_ld)
+        self.loss_rows = self.new(B)
+        if self.model == "joint":
+            d = self.im_features + self.rnn_size
+            self.concat, self.dense = self.new(B, d), self.new(B, self.fc_size)
+            if tr:
+                self.dconcat, self.ddense = self.new(B, d), self.new(B, self.fc_size)
+        elif self.model == "text" and tr:
+            self._dtxt = self.new(B, self.rnn_size)
+
+    def logits_view(self) -> View:
+        return View(self.logits, self.nb_emotions, 0)
+
+    # -- forward ---------------------------------------------------------------------------------------------
+    def forward(self, train: bool = True):
+        B = self.batch
+        if self.has_image:
+            for node in self.nodes:
+                node.fwd(train)
+            mask = None
+            if train and self.dropout != "none":
+                if self.dropout == "rng":
+                    ops.dropout_mask(self.drop_mask, DROPOUT_KEEP, self.seed + 0x5EED, self.drop_counter)
+                mask = self.drop_mask
+            hw = self.tower_h * self.tower_h
+            ops.avgpool_dropout_fwd(self.tower_out, B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, View(self.feat))
+            wl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/weights").view(self.tower_c, self.tower_classes)
+            bl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/biases")
+            dst = View(self.concat, self.im_features, 0) if self.model == "joint" else self.logits_view()
+            ops.gemm_nn(View(self.feat), View(wl), dst, bias=bl)
+        if self.has_text:
+            self.text_fwd(train)
+        if self.model == "joint":
+            ops.copy2d(self.text_feat, View(self.concat, self.rnn_size, self.im_features))
+            ops.gemm_nn(View(self.concat), View(self.weight("W_fc")), View(self.dense), bias=self.weight("b_fc"), flags=ops.EPI_RELU)
+            ops.gemm_nn(View(self.dense), View(self.weight("W_softmax")), self.logits_view(), bias=self.weight("b_softmax"))
+        elif self.model == "text":
+            ops.gemm_nn(self.text_feat, View(self.weight("W_softmax")), self.logits_view(), bias=self.weight("b_softmax"))
+
+    def loss_and_grad(self):
+        """softmax-xent (mean over the batch) + L2 of every conv weight; dlogits = (softmax - onehot)/B."""
+        B = self.batch
+        dl = View(self.dlogits, self.nb_emotions, 0)
+        ops.softmax_xent(self.logits_view(), self.labels, 1.0 / B, self.loss_rows, dl)
+        ops.reduce_sum(self.loss_rows, 1.0 / B, self.loss_buf[1:2])
+        if self.has_image:
+            ops.sumsq(self.params[:self.l2_len], 0.5 * WEIGHT_DECAY, self.loss_buf[2:3])
+        ops.reduce_sum(self.loss_buf[1:4], 1.0, self.loss_buf[0:1])
+
+    # -- backward --------------------------------------------------------------------------------------------
+    def backward(self):
+        B = self.batch
+        dl = View(self.dlogits, self.nb_emotions, 0)
+        if self.model == "joint":
+            ops.gemm_tn(View(self.dense), dl, View(self.grad("W_softmax")))
+            ops.colsum(dl, self.grad("b_softmax"))
+            ops.gemm_nt(dl, View(self.weight("W_softmax")), View(self.ddense))
+            ops.relu_bwd(self.ddense, self.dense)
+            ops.gemm_tn(View(self.concat), View(self.ddense), View(self.grad("W_fc")))
+            ops.colsum(View(self.ddense), self.grad("b_fc"))
+            ops.gemm_nt(View(self.ddense), View(self.weight("W_fc")), View(self.dconcat))
+            d_img = View(self.dconcat, self.im_features, 0)
+            d_txt = View(self.dconcat, self.rnn_size, self.im_features)
+        elif self.model == "text":
+            ops.gemm_tn(self.text_feat, dl, View(self.grad("W_softmax")))
+            ops.colsum(dl, self.grad("b_softmax"))
+            ops.gemm_nt(dl, View(self.weight("W_softmax")), View(self._dtxt))
+            d_img, d_txt = None, View(self._dtxt)
+        else:
+            d_img, d_txt = dl, None
+        if self.has_text:
+            self.text_bwd(d_txt)
+        if self.has_image:
+            wl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/weights").view(self.tower_c, self.tower_classes)
+            ops.gemm_tn(View(self.feat), d_img, View(self.grad("InceptionV1/Logits/Conv2d_0c_1x1/weights").view(self.tower_c, self.tower_classes)))
+            ops.colsum(d_img, self.grad("InceptionV1/Logits/Conv2d_0c_1x1/biases"))
+            ops.gemm_nt(d_img, View(wl), View(self.dfeat))
+            mask = self.drop_mask if self.dropout != "none" else None
+            hw = self.tower_h * self.tower_h
+            ops.avgpool_dropout_bwd(View(self.dfeat), B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, self.d_tower_out)
+            for node in reversed(self.nodes):
+                node.bwd()
+
+    # -- optimiser -------------------------------------------------------------------------------------------
+    def set_lr(self, lr: float):
+        """host side of ApplyAdam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t) for the step about to run"""
+        t = self.adam_t + 1
+        lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        ops.fill_hyper(self.hyper, lr_t, 0.9, 0.999, 1e-8, 1.0 / self.world_size)   # by-value kernel args: stream ordered
+
+    def apply_gradients(self):
+        if self.has_image:   # d(L2)/dW on the trainable conv weights, counted once (not per replica)
+            ops.axpy(self.grads[:self.l2_len], self.params[:self.l2_len], WEIGHT_DECAY * self.world_size)
+        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, self.hyper)
+        self.refresh_operands(everything=False)
+
+    def zero_step_buffers(self):
+        if self.has_image:
+            self.stats.zero_()
+            self.sums.zero_()
+
+    def fwd_bwd(self):
+        self.zero_step_buffers()
+        self.forward(train=True)
+        self.loss_and_grad()
+        self.backward()
+
+    def train_step(self, lr: float, allreduce=None) -> None:
+        """one slim.learning train_step: loss, gradients, UPDATE_OPS, Adam (eager launch sequence)"""
+        self.set_lr(lr)
+        self.fwd_bwd()
+        if allreduce is not None:
+            allreduce(self.grads)
+        self.apply_gradients()
+        self.adam_t += 1
+
+    # -- CUDA graph ----------------------------------------------------------------------------------------
+    def capture(self, allreduce=None):
+        """Capture the step into CUDA graphs (one when single-GPU; fwd+bwd | update around the all-reduce otherwise)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.fwd_bwd()                      # warm-up outside capture (lazy module loading, attribute setting)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g1):
+            self.fwd_bwd()
+            if allreduce is None:
+                self.apply_gradients()
+        self._g2 = None
+        if allreduce is not None:
+            self._g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g2):
+                self.apply_gradients()
+        self._allreduce = allreduce
+        self._graph = True
+
+    def train_step_graph(self, lr: float):
+        self.set_lr(lr)
+        self._g1.replay()
+        if self._g2 is not None:
+            self._allreduce(self.grads)
+            self._g2.replay()
+        self.adam_t += 1
+
+    # -- convenience -----------------------------------------------------------------------------------------
+    def set_batch(self, images=None, ids=None, seq_lens=None, labels=None):
+        if images is not None:
+            self.images.copy_(images, non_blocking=True)
+        if ids is not None:
+            self.ids.copy_(ids, non_blocking=True)
+        if seq_lens is not None:
+            self.seq_lens.copy_(seq_lens, non_blocking=True)
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+
+    def total_loss(self) -> float:
+        return float(self.loss_buf[0].item())
+
+    def get_logits(self) -> torch.Tensor:
+        return self.logits[:, :self.nb_emotions]
+
+    def memory_bytes(self) -> int:
+        return self._bytes

@@ -203,3 +203,7 @@ def round_tf32(x: torch.Tensor):
 
 def adam(p, g, m, v, hyper):
     lib().adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), hyper.data_ptr(), _stream())
+
+
+def fill_hyper(hyper, lr_t, beta1, beta2, eps, grad_scale):
+    lib().fill_hyper(hyper.data_ptr(), lr_t, beta1, beta2, eps, grad_scale, _stream())
