@@ -29,7 +29,7 @@ const char* ds_last_error(void);
 int ds_init(int device);
 int ds_sm_count(void);
 /* development knobs (0 = default): key 0 = im2col base-coordinate convention, 1 = force N tile, 2 = force stages,
- * 3 = shared-memory budget per CTA in KB */
+ * 3 = shared-memory budget per CTA in KB; key 15 (read-only use) counts the kernels launched by this library */
 int ds_debug_set(int key, int value);
 int ds_debug_get(int key);
 

@@ -206,7 +206,7 @@ def test_bn_forward_backward(K, m, n):
     dyd = dy.to(DEV)
     K.bn_relu_bwd_reduce(K.View(dyd), K.View(zd), mean, rstd, beta.to(DEV), sums, n)
     K.bn_relu_bwd_apply(K.View(dyd), K.View(zd), mean, rstd, beta.to(DEV), sums, n, dbeta)
-    close_frac(zd, zr.grad, 2e-4, 1e-4, "bn bwd dz"); close(dbeta, br.grad, 1e-3, "dbeta")
+    close_frac(zd, zr.grad, 2e-4, 1e-4, "bn bwd dz"); close(dbeta, br.grad, 1e-2, "dbeta")
     # inference mode (moving statistics, no update)
     yi = torch.zeros(m, n, device=DEV)
     K.bn_apply_relu(K.View(z.to(DEV)), mm.to(DEV), mv.to(DEV), O.BN_EPS, beta.to(DEV), K.View(yi), flags=K.BN_USE_VAR)

@@ -1,0 +1,301 @@
+"""The reference's Python call surface, re-hosted on the B200 engine.
+
+Mirrors (same names, positional arguments, prints and files):
+  image_text_model/im_text_rnn_model.py : _CONFIG :24-35, DeepSentiment :38-105, train_deep_sentiment :107-169,
+                                          correlation_matrix :342-376
+  image_model/im_model.py               : _CONFIG :20-25, ImageModel :139-164, train_image_model :166-225, get_init_fn :118-137
+  text_model/text_embedding.py          : _CONFIG :16-24, TextModel :37-86, train_text_model :89-150
+The TF graph objects become eager objects: `.logits`, `.labels`, `.concat_features` are torch tensors refreshed by
+every step.  Extra config keys (never renamed ones): 'precision' ('tf32' | 'fp32'), 'synthetic' (bool), 'num_samples',
+'num_classes', 'vocab_size', 'seed'.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .data import SyntheticPosts, open_split
+from .engine import Engine
+from .topology import IMAGE_SIZE, POST_SIZE
+
+_POST_SIZE = POST_SIZE
+_RANDOM_SEED = 0        # image_model/im_model.py:19
+
+DEEP_SENTIMENT_CONFIG = {'mode': 'train', 'dataset_dir': 'data', 'text_dir': 'text_model', 'emb_dir': 'embedding_weights',
+                         'filename': 'glove.6B.50d.txt', 'initial_lr': 1e-3, 'decay_factor': 0.3, 'batch_size': 64,
+                         'im_features_size': 256, 'rnn_size': 1024, 'final_endpoint': 'Mixed_5c', 'fc_size': 512}
+IMAGE_CONFIG = {'mode': 'train', 'dataset_dir': 'data', 'initial_lr': 1e-3, 'decay_factor': 0.3, 'batch_size': 64,
+                'final_endpoint': 'Mixed_5c'}
+TEXT_CONFIG = {'mode': 'train', 'dataset_dir': 'data', 'text_dir': 'text_model', 'emb_dir': 'embedding_weights',
+               'filename': 'glove.6B.50d.txt', 'initial_lr': 1e-3, 'decay_factor': 0.3, 'batch_size': 64, 'rnn_size': 1024}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distributed plumbing (one process per GPU; torch.distributed / NCCL only moves the flat gradient arena)
+# ---------------------------------------------------------------------------------------------------------------
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _maybe_init_dist():
+    import torch.distributed as dist
+    rank, world, local = _dist_env()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def make_allreduce(world: int):
+    """flat NCCL sum over the gradient arena; the 1/world mean is folded into the Adam kernel"""
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+
+    def allreduce(flat: torch.Tensor):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return allreduce
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# checkpoints: name-compatible .npz state dicts (TF variable names)
+# ---------------------------------------------------------------------------------------------------------------
+def save_checkpoint(engine: Engine, train_dir: str, step: int) -> str:
+    path = os.path.join(train_dir, "model.ckpt-%d.npz" % step)
+    sd = {k: v.numpy() for k, v in engine.state_dict().items()}
+    sd["global_step"] = np.asarray(step, dtype=np.int64)
+    np.savez(path, **sd)
+    with open(os.path.join(train_dir, "checkpoint"), "w") as f:
+        f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+    return path
+
+
+def latest_checkpoint(checkpoint_dir: str) -> Optional[str]:
+    """tf.train.latest_checkpoint analogue (im_text_rnn_model.py:354)"""
+    idx = os.path.join(checkpoint_dir, "checkpoint")
+    if os.path.exists(idx):
+        line = open(idx).readline()
+        name = line.split('"')[1] if '"' in line else line.strip()
+        path = os.path.join(checkpoint_dir, name)
+        if os.path.exists(path):
+            return path
+    cands = sorted(glob.glob(os.path.join(checkpoint_dir, "model.ckpt-*.npz")),
+                   key=lambda p: int(p.rsplit("-", 1)[1].split(".")[0]))
+    return cands[-1] if cands else None
+
+
+def load_checkpoint(engine: Engine, path: str, exclude_prefixes=(), strict: bool = True):
+    with np.load(path) as z:
+        sd = {k: torch.from_numpy(z[k]) for k in z.files if k != "global_step"}
+    engine.load_state_dict(sd, strict=strict, exclude_prefixes=tuple(exclude_prefixes))
+
+
+def get_init_fn(checkpoints_dir, model_name='inception_v1.ckpt'):
+    """image_model/im_model.py:118-137: warm start of every model variable outside InceptionV1/Logits|AuxLogits.
+    TensorFlow checkpoints cannot be parsed offline; the same variables are read from `<model_name>.npz` (an export
+    keyed by the TF variable names).  Returns fn(engine)."""
+    exclusions = ("InceptionV1/Logits", "InceptionV1/AuxLogits")
+    path = os.path.join(checkpoints_dir or "", model_name + ".npz")
+
+    def init_fn(engine: Engine):
+        if not os.path.exists(path):
+            print("No warm-start file %s: keeping the initialiser values" % path)
+            return False
+        with np.load(path) as z:
+            sd = {k: torch.from_numpy(z[k]) for k in z.files if k.startswith("InceptionV1/") and not k.startswith(exclusions)}
+        engine.load_state_dict(sd, strict=False)
+        return True
+    return init_fn
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# model objects
+# ---------------------------------------------------------------------------------------------------------------
+class _Model:
+    kind = "joint"
+
+    def __init__(self, config: Dict):
+        self.config = config
+        mode = config['mode']
+        rank, world, local = _dist_env()
+        self.rank, self.world = rank, world
+        self.learning_rate = float(config['initial_lr'])
+        self.dataset = open_split(mode, config['dataset_dir'], config, rank=rank, world=world,
+                                  with_images=self.kind != "text", with_text=True)
+        self.nb_emotions = self.dataset.num_classes
+        is_training = (mode == 'train')
+        self.is_training = is_training
+        kw = dict(model=self.kind, batch=int(config['batch_size']), nb_emotions=self.nb_emotions,
+                  precision=config.get('precision', 'tf32'), device=local, seed=int(config.get('seed', _RANDOM_SEED)),
+                  world_size=world, training=is_training, dropout="rng" if is_training else "none")
+        if self.kind != "text":
+            kw['final_endpoint'] = config['final_endpoint']
+        if self.kind != "image":
+            kw.update(rnn_size=int(config['rnn_size']), vocab=self.dataset.vocab_size, emb_dim=self.dataset.embedding_dim)
+            self.embedding = self.dataset.embedding            # [vocab, 50] incl. the <ukn> zero row
+        if self.kind == "joint":
+            kw.update(im_features=int(config['im_features_size']), fc_size=int(config['fc_size']))
+        self.engine = Engine(**kw)
+        self.logits = self.engine.get_logits()
+        self.labels = self.engine.labels
+        self.post_ids = None
+        self.days = None
+        if self.kind == "joint":
+            self.concat_features = self.engine.concat
+
+    # the reference's lr_rate_assign op
+    def lr_rate_assign(self, value: float):
+        self.learning_rate = float(value)
+
+    def embedding_init(self):
+        """W_embedding.assign(embedding_placeholder) (im_text_rnn_model.py:83-84, run at step 0 :150-151)"""
+        self.engine.load_state_dict({"Text/W_embedding": torch.as_tensor(self.embedding, dtype=torch.float32)}, strict=False)
+
+    def feed(self, batch: Dict[str, torch.Tensor]):
+        e = self.engine
+        e.set_batch(batch.get("images") if e.has_image else None, batch.get("ids") if e.has_text else None,
+                    batch.get("seq_lens") if e.has_text else None, batch["labels"])
+        self.post_ids, self.days = batch.get("post_ids"), batch.get("days")
+
+
+class DeepSentiment(_Model):
+    kind = "joint"
+
+
+class ImageModel(_Model):
+    kind = "image"
+
+
+class TextModel(_Model):
+    kind = "text"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trainers
+# ---------------------------------------------------------------------------------------------------------------
+def _train(model_cls, config, checkpoints_dir, train_dir, num_steps, use_init_fn, log_every=None):
+    rank, world, _ = _maybe_init_dist()
+    if rank == 0:
+        if os.path.exists(train_dir):
+            shutil.rmtree(train_dir)          # "Delete old model" (im_text_rnn_model.py:116-119)
+        os.makedirs(train_dir)
+    model = model_cls(config)
+    eng = model.engine
+    if use_init_fn:
+        get_init_fn(checkpoints_dir)(eng)
+    if world > 1:                             # replicas start from rank 0's variables
+        import torch.distributed as dist
+        for t in (eng.params, eng.moving_mean, eng.moving_var) if eng.has_image else (eng.params,):
+            dist.broadcast(t, 0)
+        eng.refresh_operands(everything=True)
+    allreduce = make_allreduce(world)
+    batch_size = int(config['batch_size'])
+    initial_lr, decay_factor = config['initial_lr'], config['decay_factor']
+    nb_batches = max(model.dataset.num_samples // batch_size, 1)      # py2 integer division (:140)
+    step = epoch = 0
+    use_graph = bool(config.get('cuda_graph', True))
+    if use_graph:
+        model.feed(model.dataset.next_batch(batch_size))
+        eng.capture(allreduce)
+        eng.adam_t = 0
+    last_save = time.time()
+    total_loss = float("nan")
+    t0 = time.time()
+    while step < num_steps:
+        if step % nb_batches == 0:            # decaying learning rate every epoch (:143-147)
+            lr_decay = decay_factor ** epoch
+            model.lr_rate_assign(initial_lr * lr_decay)
+            if rank == 0:
+                print('New learning rate: {0}'.format(initial_lr * lr_decay))
+            epoch += 1
+        if step == 0 and model.kind != "image":
+            model.embedding_init()
+        model.feed(model.dataset.next_batch(batch_size))
+        if use_graph:
+            eng.train_step_graph(model.learning_rate)
+        else:
+            eng.train_step(model.learning_rate, allreduce)
+        step += 1
+        if log_every and step % log_every == 0 or step == num_steps:
+            total_loss = eng.total_loss()
+            if rank == 0 and log_every:
+                dt = (time.time() - t0) / step
+                print('global step %d: loss = %.4f (%.3f sec/step)' % (step, total_loss, dt))
+        if rank == 0 and time.time() - last_save > 600:      # save_interval_secs=600 (:164)
+            save_checkpoint(eng, train_dir, step)
+            last_save = time.time()
+    if rank == 0:
+        save_checkpoint(eng, train_dir, step)
+        print('Finished training. Last batch loss {0:.3f}'.format(total_loss))
+    return total_loss
+
+
+def train_deep_sentiment(checkpoints_dir, train_dir, num_steps, _config=None):
+    """Fine tune the inception model, retraining the last layer (im_text_rnn_model.py:107-169)."""
+    _train(DeepSentiment, _config or DEEP_SENTIMENT_CONFIG, checkpoints_dir, train_dir, num_steps, True)
+
+
+def train_image_model(checkpoints_dir, train_dir, num_steps, _config=None):
+    """Fine tune the Image model, retraining Mixed_5c (im_model.py:166-225)."""
+    _train(ImageModel, _config or IMAGE_CONFIG, checkpoints_dir, train_dir, num_steps, True)
+
+
+def train_text_model(train_dir, num_steps, _config=None):
+    """Train rnn text model (text_embedding.py:89-150); no init_fn."""
+    _train(TextModel, _config or TEXT_CONFIG, None, train_dir, num_steps, False)
+
+
+def correlation_matrix(nb_batches, checkpoint_dir, _config=None, out_dir='data'):
+    """Computes logits and labels of the input posts and saves them as numpy files (im_text_rnn_model.py:342-376).
+    Forward only: is_training=False -> BN on moving statistics, no dropout.  Under torchrun the posts are sharded
+    across ranks (no collective on the data path) and gathered on rank 0."""
+    rank, world, _ = _maybe_init_dist()
+    config = dict(_config or DEEP_SENTIMENT_CONFIG)
+    config['mode'] = 'validation'
+    model = DeepSentiment(config)
+    eng = model.engine
+    path = latest_checkpoint(checkpoint_dir) if checkpoint_dir else None
+    if path:
+        load_checkpoint(eng, path)
+    elif rank == 0:
+        print("No checkpoint under %r: using the initialiser values" % (checkpoint_dir,))
+    batch_size = int(config['batch_size'])
+    my_batches = [i for i in range(nb_batches) if i % world == rank]
+    logits_dev = torch.empty(len(my_batches), batch_size, eng.nb_emotions, device=eng.device)
+    labels_dev = torch.empty(len(my_batches), batch_size, dtype=torch.int64, device=eng.device)
+    for j, _ in enumerate(my_batches):
+        model.feed(model.dataset.next_batch(batch_size))
+        eng.forward(train=False)
+        logits_dev[j].copy_(eng.get_logits())
+        labels_dev[j].copy_(eng.labels)
+    posts_logits = logits_dev.reshape(-1, eng.nb_emotions)
+    posts_labels = labels_dev.reshape(-1)
+    if world > 1:
+        import torch.distributed as dist
+        n_max = -(-nb_batches // world) * batch_size
+        pad_l = torch.zeros(n_max, eng.nb_emotions, device=eng.device); pad_l[:posts_logits.shape[0]] = posts_logits
+        pad_y = torch.full((n_max,), -1, dtype=torch.int64, device=eng.device); pad_y[:posts_labels.shape[0]] = posts_labels
+        gl = [torch.empty_like(pad_l) for _ in range(world)]; gy = [torch.empty_like(pad_y) for _ in range(world)]
+        dist.all_gather(gl, pad_l); dist.all_gather(gy, pad_y)
+        keep = [g >= 0 for g in gy]
+        # restore batch order i = 0..nb_batches-1 (batch i lives on rank i % world)
+        per_rank_l = [g[k].view(-1, batch_size, eng.nb_emotions) for g, k in zip(gl, keep)]
+        per_rank_y = [g[k].view(-1, batch_size) for g, k in zip(gy, keep)]
+        posts_logits = torch.cat([per_rank_l[i % world][i // world] for i in range(nb_batches)])
+        posts_labels = torch.cat([per_rank_y[i % world][i // world] for i in range(nb_batches)])
+    posts_logits, posts_labels = posts_logits.cpu().numpy(), posts_labels.cpu().numpy()
+    if rank == 0 and out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+        np.save(os.path.join(out_dir, 'posts_logits.npy'), posts_logits)
+        np.save(os.path.join(out_dir, 'posts_labels.npy'), posts_labels)
+    return posts_logits, posts_labels

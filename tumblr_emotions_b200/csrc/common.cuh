@@ -21,6 +21,7 @@ extern int g_debug[16];
 
 #define DS_LAUNCH_CHECK()                                                                    \
   do {                                                                                       \
+    ++ds::g_debug[15]; /* kernel-launch counter (ds_debug_get(15)) */                        \
     cudaError_t _e = cudaPeekAtLastError();                                                  \
     if (_e != cudaSuccess) {                                                                 \
       cudaGetLastError();                                                                    \

@@ -630,6 +630,8 @@ class Engine:
             self.fwd_bwd()                      # warm-up outside capture (lazy module loading, attribute setting)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        from ._lib import lib
+        n0 = lib().debug_get(15)
         self._g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g1):
             self.fwd_bwd()
@@ -640,6 +642,7 @@ class Engine:
             self._g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._g2):
                 self.apply_gradients()
+        self.launches_per_step = lib().debug_get(15) - n0      # kernels of this library inside one captured step
         self._allreduce = allreduce
         self._graph = True
 
