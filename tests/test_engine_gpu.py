@@ -1,8 +1,9 @@
 """End-to-end parity of the CUDA training step (Engine, through the C ABI) against the CPU oracle on the same seeded
 inputs and parameters: logits, loss, every trainable gradient, Adam-updated parameters and BN moving statistics.
 
-Tolerances: the fp32 (SIMT) build is held to 1e-4; the TF32 tensor-core build to the 1e-3 relative logit bound of
-BASELINE.json `north_star` (gradients 3e-2 relative to each tensor's max, since they pass through 22 TF32 layers twice).
+Tolerances: logits/loss of the fp32 (SIMT) build within 1e-4 and of the TF32 tensor-core build within the 1e-3 relative bound
+of BASELINE.json `north_star`, both against the oracle evaluated in float64; gradients are bounded relative to the error the
+fp32 oracle itself makes against that float64 truth (see run_steps).
 """
 import pytest
 import torch
@@ -23,9 +24,7 @@ def row_rel_l2(got, ref):
     return ((got - ref).norm(dim=1) / (ref.norm(dim=1) + 1e-30)).max().item()
 
 
-def make(model, batch, precision, seed=0, **kw):
-    from tumblr_emotions_b200.engine import Engine
-    eng = Engine(model=model, batch=batch, precision=precision, vocab=VOCAB, dropout="given" if model != "text" else "none", **kw)
+def _start_state(model, batch, seed=0):
     p = O.init_params(seed, model, vocab=VOCAB)
     # non-trivial BN state so that beta / moving statistics matter
     g = torch.Generator().manual_seed(99)
@@ -36,84 +35,110 @@ def make(model, batch, precision, seed=0, **kw):
             p[k] = torch.randn(p[k].shape, generator=g) * 0.05
         elif k.endswith("/moving_variance"):
             p[k] = torch.rand(p[k].shape, generator=g) * 0.5 + 0.75
-    eng.load_state_dict(p)
     batch_d = O.synthetic_batch(batch, seed=1234, vocab=VOCAB, with_images=(model != "text"))
-    eng.set_batch(batch_d.get("images"), batch_d.get("ids") if model != "image" else None,
-                  batch_d.get("seq_lens") if model != "image" else None, batch_d["labels"])
     mask = None
     if model != "text":
         mask = (torch.rand(batch, 1024, generator=g) < 0.8).float()
+    return p, batch_d, mask
+
+
+def _to64(d):
+    return {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+
+
+def make(model, batch, precision, seed=0, **kw):
+    from tumblr_emotions_b200.engine import Engine
+    eng = Engine(model=model, batch=batch, precision=precision, vocab=VOCAB, dropout="given" if model != "text" else "none", **kw)
+    p, batch_d, mask = _start_state(model, batch, seed)
+    eng.load_state_dict(p)
+    eng.set_batch(batch_d.get("images"), batch_d.get("ids") if model != "image" else None,
+                  batch_d.get("seq_lens") if model != "image" else None, batch_d["labels"])
+    if mask is not None:
         eng.drop_mask.copy_(mask)
         mask = mask.view(batch, 1, 1, 1024)
     return eng, p, batch_d, mask
 
 
-def run_steps(model, precision, steps, tol_logits, tol_grad_l2, tol_param_mean, batch=3):
-    """Gradients and Adam-updated parameters are compared with norm-wise / distribution statistics: a ReLU or max-pool
-    input that sits within rounding distance of its switching point legitimately flips between two correct
-    implementations, which moves single gradient entries by O(1) and (through Adam's g/|g| normalisation) single
-    parameters by up to 2*lr, while leaving every norm-wise quantity untouched."""
-    eng, p, bd, mask = make(model, batch, precision)
+def _grad_errors(get, truth, names):
+    """(global rel-L2, {name: rel-L2}) of gradients `get(name)` against the fp64 truth"""
+    num = den = 0.0
+    per = {}
+    for n in names:
+        g, r = get(n).detach().double().cpu(), truth[n].double()
+        d2, r2 = float(((g - r) ** 2).sum()), float((r ** 2).sum())
+        num += d2; den += r2
+        if r2 > 0:
+            per[n] = (d2 / r2) ** 0.5
+    return (num / max(den, 1e-300)) ** 0.5, per
+
+
+def run_steps(model, precision, steps, tol_logits, grad_factor, grad_floor, tol_param_mean, batch=3):
+    """Truth = the oracle evaluated in float64.  Yardstick = the error of the *same oracle in float32* against that truth:
+    the batch-norm beta gradients of this network are badly conditioned (the following BN cancels all but the
+    ReLU-gated part of a channel shift), so a correct fp32 implementation is itself ~1e-3 (global) / ~1e-2 (single beta
+    tensors) away from exact arithmetic.  The CUDA step must be within `grad_factor` x that yardstick (floor
+    `grad_floor`), logits within `tol_logits` of the truth.  A ReLU / max-pool input within rounding distance of its
+    switching point may flip between two correct implementations, so 10% of the tensors may exceed the bound (by <= 20x)
+    and Adam-updated parameters are compared as max |d| <= 2*lr per step and a mean |d| bound."""
+    eng, p32, bd, mask = make(model, batch, precision)
     assert eng.n_trainable() == {"joint": 6680959, "image": 1367167, "text": 4418575}[model]
-    names = O.trainable_names(p)
+    names = O.trainable_names(p32)
     assert sorted(names) == sorted(eng.trainable_names())
-    opt = O.TFAdam(names, p)
+    p64, bd64 = _to64(p32), _to64(bd)
+    mask64 = mask.double() if mask is not None else None
+    opt32, opt64 = O.TFAdam(names, p32), O.TFAdam(names, p64)
     lr = 1e-3
     for step in range(steps):
-        loss_ref, logits_ref, grads_ref = O.train_step(model, p, opt, lr, bd, mask)
+        _, _, grads32 = O.train_step(model, p32, opt32, lr, bd, mask)
+        loss_ref, logits_ref, grads_ref = O.train_step(model, p64, opt64, lr, bd64, mask64)
         eng.train_step(lr)
         torch.cuda.synchronize()
         e_log = row_rel_l2(eng.get_logits(), logits_ref)
         e_loss = abs(eng.total_loss() - float(loss_ref)) / max(1.0, abs(float(loss_ref)))
-        num = den = 0.0
-        per = []
-        for n in names:
-            g, r = eng.tensor(n, "grads").detach().double().cpu(), grads_ref[n].double()
-            d2, r2 = float(((g - r) ** 2).sum()), float((r ** 2).sum())
-            num += d2; den += r2
-            if r2 > 0:
-                per.append(((d2 / r2) ** 0.5, n))
-        g_l2 = (num / max(den, 1e-300)) ** 0.5
-        per.sort(reverse=True)
-        frac_ok = sum(1 for e, _ in per if e <= tol_grad_l2) / max(len(per), 1)
+        base_g, base_per = _grad_errors(lambda n: grads32[n], grads_ref, names)
+        g_l2, per = _grad_errors(lambda n: eng.tensor(n, "grads"), grads_ref, names)
+        bound = {n: max(grad_floor, grad_factor * base_per.get(n, 0.0)) for n in per}
+        ratio = sorted(((per[n] / bound[n], n) for n in per), reverse=True)
+        frac_ok = sum(1 for r, _ in ratio if r <= 1.0) / max(len(ratio), 1)
         dmax = dmean = 0.0
         cnt = 0
         for n in names:
-            d = (eng.tensor(n).detach().double().cpu() - p[n].double()).abs()
+            d = (eng.tensor(n).detach().double().cpu() - p64[n]).abs()
             dmax = max(dmax, float(d.max())); dmean += float(d.sum()); cnt += d.numel()
         dmean /= cnt
-        print("[%s/%s step %d] logits rel-L2 %.2e  loss rel %.2e  grads global rel-L2 %.2e (worst %s %.2e, %.0f%% of tensors within %.0e)  "
-              "params max|d| %.2e mean|d| %.2e" % (model, precision, step, e_log, e_loss, g_l2, per[0][1], per[0][0], 100 * frac_ok,
-                                                    tol_grad_l2, dmax, dmean))
+        print("[%s/%s step %d] logits rel-L2 %.2e  loss rel %.2e  grads global rel-L2 %.2e (fp32 oracle: %.2e)  worst tensor %s %.2e "
+              "(fp32 oracle: %.2e), %.0f%% of tensors within bound  params max|d| %.2e mean|d| %.2e"
+              % (model, precision, step, e_log, e_loss, g_l2, base_g, ratio[0][1], per[ratio[0][1]], base_per.get(ratio[0][1], 0.0),
+                 100 * frac_ok, dmax, dmean))
         assert e_log <= tol_logits, "step %d logits rel-L2 %.3e" % (step, e_log)
         assert e_loss <= tol_logits, (eng.total_loss(), float(loss_ref))
-        assert g_l2 <= tol_grad_l2, "step %d global gradient rel-L2 %.3e" % (step, g_l2)
-        assert frac_ok >= 0.9 and per[0][0] <= 20 * tol_grad_l2, "step %d gradient tensors: %s" % (step, per[:5])
+        assert g_l2 <= max(grad_floor, grad_factor * base_g), "step %d global gradient rel-L2 %.3e (fp32 oracle %.3e)" % (step, g_l2, base_g)
+        assert frac_ok >= 0.9 and ratio[0][0] <= 20, "step %d gradient tensors: %s" % (step, ratio[:5])
         assert dmax <= 2.1 * lr * (step + 1) and dmean <= tol_param_mean, "step %d params max|d| %.3e mean|d| %.3e" % (step, dmax, dmean)
         if model != "text":
-            for n in p:
+            for n in p64:
                 if n.endswith(("moving_mean", "moving_variance")):
-                    assert rel_err(eng.tensor(n), p[n]) <= max(tol_logits, 1e-5), n
+                    assert rel_err(eng.tensor(n), p64[n]) <= max(tol_logits, 1e-5), n
 
 
 def test_joint_fp32_two_steps():
-    run_steps("joint", "fp32", 2, 1e-4, 5e-3, 2e-6)
+    run_steps("joint", "fp32", 2, 1e-4, 3.0, 1e-4, 2e-6)
 
 
 def test_joint_tf32_two_steps():
-    run_steps("joint", "tf32", 2, 1e-3, 8e-2, 5e-5)
+    run_steps("joint", "tf32", 2, 1e-3, 30.0, 2e-2, 5e-5)
 
 
 def test_image_tf32_one_step():
-    run_steps("image", "tf32", 1, 1e-3, 8e-2, 5e-5)
+    run_steps("image", "tf32", 1, 1e-3, 30.0, 2e-2, 5e-5)
 
 
 def test_text_tf32_two_steps():
-    run_steps("text", "tf32", 2, 1e-3, 1e-2, 2e-5, batch=5)
+    run_steps("text", "tf32", 2, 1e-3, 30.0, 1e-2, 2e-5, batch=5)
 
 
 def test_text_fp32_two_steps():
-    run_steps("text", "fp32", 2, 1e-4, 1e-3, 2e-6, batch=5)
+    run_steps("text", "fp32", 2, 1e-4, 3.0, 1e-4, 2e-6, batch=5)
 
 
 def test_inference_forward_matches_oracle():
