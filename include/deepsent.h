@@ -52,6 +52,52 @@ int ds_conv_tc(const float* a, int64_t lda, int64_t batch, int64_t h, int64_t w,
                const float* bt, int64_t ldb, int64_t n, float* c, int64_t ldc,
                const float* scale, const float* bias, double* stats, int flags, void* stream);
 
+/* ---- split-bf16 contractions (the product path) ---------------------------------------------------
+ * Operand format: a value x is carried as two bf16 planes, x ~= hi + lo (hi = bf16(x), lo = bf16(x - hi)); a plane pair is
+ * passed as two pointers with one shared leading dimension (in bf16 elements).  An activation [pixels, C] is normally stored
+ * with its planes interleaved per pixel, [hi(C) | lo(C)], i.e. lda = 2*C and a_lo = a_hi + C - the same 4 bytes per value as
+ * fp32.
+ *
+ * ds_conv_bf16x3: persistent warp-specialised tcgen05 kernel (kind::f16, fp32 accumulate in TMEM), stride 1, TF-"SAME":
+ *   C[m, n] = epi( sum_{r,s,c} A[pixel(m) + (r-p, s-p), c] * Bt[n, (r*ks+s)*cin + c] ),   A*B := Ahi*Bhi + Alo*Bhi + Ahi*Blo
+ * A: NHWC activation slice [batch, h, w, cin] with pixel stride lda (1x1: plain [M,K] GEMM; 3x3: TMA im2col mode).
+ * Bt: K-major weights [N, ks*ks*cin], row stride ldb.  C: fp32 [M, ldc].  epi: acc*scale[n] + bias[n] (either may be NULL),
+ * then flags.  ksplit > 1 splits the reduction over CTAs and ADDS atomically into C (caller zeroes C; no ReLU / stats).
+ * Replaces slim.conv2d 1x1/3x3 sites image_model/inception_v1.py:71-247 (fwd), their tf.gradients input gradients
+ * (Conv2DBackpropInput == same contraction on flipped weights), the Mixed_5c weight gradients :229-248 (on transposed
+ * operands from ds_im2col_transpose_split) and the LSTM products text_model/text_embedding.py:79-80,
+ * image_text_model/im_text_rnn_model.py:89-90.
+ * Requirements: lda/ldb % 8 == 0, n % 4 == 0, ldc % 4 == 0, 16-byte aligned bases, cin % 8 == 0 when ksize == 3. */
+int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                   int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                   float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
+                   int ksplit, void* stream);
+/* fp32 [rows, cols] <-> split planes */
+int ds_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream);
+int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t rows, int64_t cols, float* out, int64_t ldo,
+                  void* stream);
+/* out[(tap*cin + c), m] = x[pixel(m) + tap - pad, c] (0 outside the image): the pixel-major (K-major) operands of the
+ * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w. */
+int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w,
+                              int64_t cin, int ksize, uint16_t* o_hi, uint16_t* o_lo, int64_t ldo, void* stream);
+/* HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld) and input-gradient operand [cin][kh'][kw'][cout]
+ * (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout: the fused sibling 1x1 convs of an inception block share
+ * one operand whose K axis is the concatenation of their output channels) as split planes; either pair may be NULL */
+int ds_repack_conv_weights_split(const float* hwio, int kh, int kw, int64_t cin, int64_t cout, uint16_t* fwd_hi, uint16_t* fwd_lo,
+                                 int64_t fwd_ld, uint16_t* dgrad_hi, uint16_t* dgrad_lo, int64_t dgrad_ld, int64_t dgrad_tap,
+                                 void* stream);
+/* split-output / split-input variants of the streaming kernels below (same arithmetic, activations in split planes) */
+int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean, const float* rstd, float eps,
+                           const float* beta, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, int flags, void* stream);
+int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
+                               const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
+                               uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
+int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,
+                         int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo, uint16_t* y_hi, uint16_t* y_lo,
+                         int64_t ldy, uint8_t* argmax, void* stream);
+int ds_avgpool_dropout_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t hw, int64_t c,
+                                 const float* mask, float inv_keep, float* out, int64_t ldo, void* stream);
+
 /* SIMT fp32 convolution (any k, stride, explicit TF-SAME pads): the 7x7/2 stem
  * (image_model/inception_v1.py:63) and the fp32 cross-check path.  Weight element ((r*kw+s)*cin+c, n) is read at
  * wgt[kidx*swk + n*swn]: HWIO is (swk=n, swn=1). */

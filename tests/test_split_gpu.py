@@ -1,0 +1,232 @@
+"""Parity tests of the split-bf16 product path (ds_conv_bf16x3 and the split-format streaming kernels), called through
+the C ABI, against the CPU oracle / float64 on the same seeded inputs.
+
+Tolerances: a split value carries 16 significant bits (relative 2^-17 after rounding) and the contraction drops the
+lo*lo term (2^-16 relative per product), so contractions of random data are held to 1e-4 of the output scale; operands that
+are exactly representable in bf16 must reproduce the fp32-accumulated product to 1e-5."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tf_semantics as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def K():
+    from tumblr_emotions_b200 import ops
+    ops.init(0)
+    return ops
+
+
+def gen(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def close(got, ref, rtol, name=""):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    scale = ref.abs().max().item() + 1e-30
+    err = (got - ref).abs().max().item()
+    assert err <= rtol * scale, "%s: max abs err %.3e vs scale %.3e (rel %.3e > %.1e)" % (name, err, scale, err / scale, rtol)
+
+
+def to_split(K, x2d):
+    """fp32 [rows, cols] (CPU) -> SView on the device via the CUDA converter"""
+    rows, cols = x2d.shape
+    buf = K.new_split((rows,), cols, DEV)
+    sv = K.SView(buf)
+    K.split_bf16(K.View(x2d.contiguous().to(DEV)), sv)
+    return sv
+
+
+def split_cpu(x):
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return hi, lo
+
+
+def test_split_merge_roundtrip(K):
+    g = gen(1)
+    x = torch.randn(300, 72, generator=g) * torch.logspace(-6, 6, 72)
+    sv = to_split(K, x)
+    hi, lo = split_cpu(x)
+    b = sv.base.view(300, 144).cpu()
+    assert torch.equal(b[:, :72], hi) and torch.equal(b[:, 72:], lo)          # bit-exact vs the CPU definition
+    out = torch.zeros(300, 72, device=DEV)
+    K.merge_bf16(sv, K.View(out))
+    rel = ((out.cpu() - x).abs() / x.abs().clamp_min(1e-30)).max().item()
+    assert rel <= 2.0 ** -16, rel
+    assert torch.equal(out.cpu(), sv.torch().cpu())
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 64, 16), (300, 64, 48), (1000, 480, 304), (256, 1024, 4096), (392, 528, 448), (200, 16, 32),
+                                   (130, 24, 64), (5, 8, 4), (50176, 96, 208), (20000, 832, 384)])
+def test_conv_bf16x3_gemm(K, m, k, n):
+    g = gen(5)
+    a = torch.rand(m, k, generator=g) * 2 - 1
+    bt = torch.rand(n, k, generator=g) * 2 - 1
+    bias = torch.randn(n, generator=g)
+    c = torch.full((m, n), 3.0, device=DEV)
+    stats = torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+    A, Bt = to_split(K, a), to_split(K, bt)
+    K.gemm_bf16x3(A, Bt, K.View(c), bias=None, flags=K.EPI_STATS if False else 0)
+    ref = a.double() @ bt.double().t()
+    close(c, ref, 1e-4, "bf16x3 gemm")
+    c.fill_(3.0)
+    K.conv_bf16x3(A, m, 1, 1, k, 1, Bt, n, K.View(c), stats=stats)
+    close(c, ref, 1e-4, "bf16x3 gemm (+stats)")
+    close(stats[:n], ref.sum(0), 1e-4, "stats sum")
+    close(stats[n:], (ref * ref).sum(0), 1e-4, "stats sumsq")
+    c.fill_(3.0)
+    K.gemm_bf16x3(A, Bt, K.View(c), bias=bias.to(DEV), flags=K.EPI_ACCUMULATE | K.EPI_RELU)
+    close(c, F.relu(ref + bias.double() + 3.0), 1e-4, "bf16x3 gemm bias+acc+relu")
+
+
+def test_conv_bf16x3_exact_on_bf16_operands(K):
+    g = gen(6)
+    m, k, n = 512, 256, 96
+    a = (torch.rand(m, k, generator=g) * 2 - 1).bfloat16().float()
+    bt = (torch.rand(n, k, generator=g) * 2 - 1).bfloat16().float()
+    c = torch.zeros(m, n, device=DEV)
+    K.gemm_bf16x3(to_split(K, a), to_split(K, bt), K.View(c))
+    close(c, a.double() @ bt.double().t(), 1e-5, "bf16-exact operands")
+
+
+def test_conv_bf16x3_beats_single_pass_precision(K):
+    """fp32 operands: the 3-term product must be ~2^-16 accurate, far below one bf16 pass (2^-8)"""
+    g = gen(7)
+    m, k, n = 256, 512, 64
+    a = torch.rand(m, k, generator=g) + 0.5
+    bt = torch.rand(n, k, generator=g) + 0.5
+    c = torch.zeros(m, n, device=DEV)
+    K.gemm_bf16x3(to_split(K, a), to_split(K, bt), K.View(c))
+    close(c, a.double() @ bt.double().t(), 3e-5, "bf16x3 on positive operands")
+
+
+def make_weights(K, w):
+    kh, kw, cin, cout = w.shape
+    fwd = K.SView(torch.zeros(cout, 2 * kh * kw * cin, dtype=torch.bfloat16, device=DEV))
+    dg = K.SView(torch.zeros(cin, 2 * kh * kw * cout, dtype=torch.bfloat16, device=DEV))
+    K.repack_conv_weights_split(w.to(DEV), fwd=fwd, dgrad=dg)
+    return fwd, dg
+
+
+@pytest.mark.parametrize("b,h,cin,cout", [(1, 8, 32, 16), (2, 14, 32, 32), (3, 14, 96, 208), (2, 7, 48, 128), (2, 28, 16, 32),
+                                          (1, 56, 64, 192), (5, 7, 24, 64), (1, 14, 112, 224), (3, 14, 160, 320)])
+def test_conv_bf16x3_3x3_matches_oracle(K, b, h, cin, cout):
+    g = gen(7)
+    x = torch.rand(b, h, h, cin, generator=g) * 2 - 1
+    w = torch.randn(3, 3, cin, cout, generator=g) * 0.1
+    fwd, _ = make_weights(K, w)
+    c = torch.full((b * h * h, cout), 3.0, device=DEV)
+    X = to_split(K, x.view(-1, cin))
+    K.conv_bf16x3(X, b, h, h, cin, 3, fwd, cout, K.View(c))
+    ref = O.conv2d(x.double(), w.double(), 1).reshape(-1, cout)
+    close(c, ref, 1e-4, "bf16x3 conv3x3")
+
+
+def test_conv_bf16x3_channel_slices_and_dgrad(K):
+    """A read from a channel slice of a wider split buffer, C written into a slice; dgrad == conv with the flipped operand"""
+    g = gen(8)
+    b, h, cin, cout = 2, 14, 24, 40
+    buf = torch.rand(b, h, h, 64, generator=g) * 2 - 1
+    w = torch.randn(3, 3, cin, cout, generator=g) * 0.1
+    fwd, dg = make_weights(K, w)
+    out = torch.zeros(b * h * h, 96, device=DEV)
+    X = to_split(K, buf.view(-1, 64))
+    K.conv_bf16x3(X.slice(16, cin), b, h, h, cin, 3, fwd, cout, K.View(out, cout, 8))
+    x = buf[..., 16:16 + cin].double()
+    close(out[:, 8:8 + cout], O.conv2d(x, w.double(), 1).reshape(-1, cout), 1e-4, "slice conv")
+    assert float(out[:, :8].abs().max()) == 0 and float(out[:, 8 + cout:].abs().max()) == 0
+    dz = torch.randn(b, h, h, cout, generator=g)
+    xg = x.clone().requires_grad_(True)
+    (O.conv2d(xg, w.double(), 1) * dz.double()).sum().backward()
+    dx = torch.zeros(b * h * h, cin, device=DEV)
+    K.conv_bf16x3(to_split(K, dz.view(-1, cout)), b, h, h, cout, 3, dg, cin, K.View(dx))
+    close(dx, xg.grad.reshape(-1, cin), 1e-4, "dgrad")
+
+
+@pytest.mark.parametrize("b,h,cin,cout,k", [(3, 7, 48, 128, 3), (2, 7, 832, 384, 1), (5, 7, 192, 384, 3), (1, 14, 16, 8, 3)])
+def test_wgrad_via_transposed_split_k(K, b, h, cin, cout, k):
+    """dW[(r,s,c), n] = sum_m X[pix(m)+(r,s), c] dZ[m, n]: im2col-transposed operands + split-K atomic epilogue"""
+    g = gen(9)
+    x = torch.randn(b, h, h, cin, generator=g)
+    dz = torch.randn(b, h, h, cout, generator=g)
+    w = torch.zeros(k, k, cin, cout, dtype=torch.float64, requires_grad=True)
+    (O.conv2d(x.double(), w, 1) * dz.double()).sum().backward()
+    M = b * h * h
+    ld = (M + 7) // 8 * 8
+    X, DZ = to_split(K, x.view(-1, cin)), to_split(K, dz.view(-1, cout))
+    At = K.SView(torch.zeros(k * k * cin, 2 * ld, dtype=torch.bfloat16, device=DEV))
+    Bt = K.SView(torch.zeros(cout, 2 * ld, dtype=torch.bfloat16, device=DEV))
+    K.im2col_transpose_split(X, b, h, h, cin, k, At)
+    K.im2col_transpose_split(DZ, b, h, h, cout, 1, Bt)
+    dw = torch.zeros(k * k * cin, cout, device=DEV)
+    K.gemm_bf16x3(At, Bt, K.View(dw), k=M, ksplit=4)
+    close(dw, w.grad.reshape(-1, cout), 1e-4, "wgrad k=%d" % k)
+
+
+@pytest.mark.parametrize("m,n", [(1000, 64), (37, 16), (5000, 304)])
+def test_bn_split_kernels_match_fp32_kernels(K, m, n):
+    g = gen(10)
+    z = torch.randn(m, n, generator=g) * 2 + 0.3
+    dy = torch.randn(m, n, generator=g)
+    beta = torch.randn(n, generator=g) * 0.2
+    zd, dyd, betad = z.to(DEV), dy.to(DEV), beta.to(DEV)
+    stats = torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+    K.colstats(K.View(zd), stats)
+    mean, rstd = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    K.bn_finalize(stats, m, n, None, None, 0.0, 1e-3, mean, rstd)
+    y32 = torch.zeros(m, n, device=DEV)
+    K.bn_apply_relu(K.View(zd), mean, rstd, 1e-3, betad, K.View(y32))
+    ys = K.SView(K.new_split((m,), n, DEV))
+    K.bn_apply_relu_split(K.View(zd), mean, rstd, 1e-3, betad, ys)
+    hi, lo = split_cpu(y32.cpu())
+    b = ys.base.view(m, 2 * n).cpu()
+    assert torch.equal(b[:, :n], hi) and torch.equal(b[:, n:], lo)
+    sums = torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+    K.bn_relu_bwd_reduce(K.View(dyd), K.View(zd), mean, rstd, betad, sums, n)
+    dzs = K.SView(K.new_split((m,), n, DEV))
+    dbeta = torch.zeros(n, device=DEV)
+    K.bn_relu_bwd_apply_split(K.View(dyd), K.View(zd), mean, rstd, betad, sums, n, dzs, dbeta)
+    z2, dbeta2 = zd.clone(), torch.zeros(n, device=DEV)
+    K.bn_relu_bwd_apply(K.View(dyd), K.View(z2), mean, rstd, betad, sums, n, dbeta2)
+    hi, lo = split_cpu(z2.cpu())
+    b = dzs.base.view(m, 2 * n).cpu()
+    assert torch.equal(b[:, :n], hi) and torch.equal(b[:, n:], lo)
+    assert torch.equal(dbeta, dbeta2)
+
+
+@pytest.mark.parametrize("b,h,c,k,s", [(2, 14, 32, 3, 1), (2, 28, 16, 3, 2), (1, 14, 8, 2, 2), (3, 7, 832, 3, 1)])
+def test_maxpool_split_matches_fp32_kernel(K, b, h, c, k, s):
+    g = gen(11)
+    x = torch.randn(b, h, h, c, generator=g)
+    hi, lo = split_cpu(x)
+    xm = hi.float() + lo.float()                        # the value the split buffer represents
+    ho, pt, _ = O.tf_same_pad(h, k, s)
+    X = to_split(K, x.view(-1, c))
+    Y = K.SView(K.new_split((b * ho * ho,), c, DEV))
+    arg = torch.zeros(b * ho * ho * c, dtype=torch.uint8, device=DEV)
+    K.maxpool_fwd_split(X, b, h, h, c, k, s, pt, pt, ho, ho, Y, arg)
+    y32 = torch.zeros(b * ho * ho, c, device=DEV)
+    arg32 = torch.zeros_like(arg)
+    K.maxpool_fwd(K.View(xm.view(-1, c).to(DEV)), b, h, h, c, k, s, pt, pt, ho, ho, K.View(y32), arg32)
+    assert torch.equal(Y.torch(), y32)
+    assert torch.equal(arg, arg32)
+    ref = O.max_pool(xm, k, s).reshape(-1, c)
+    assert torch.equal(y32.cpu(), ref)
+
+
+def test_avgpool_split(K):
+    g = gen(12)
+    b, hw, c = 3, 49, 1024
+    x = torch.randn(b * hw, c, generator=g)
+    mask = (torch.rand(b, c, generator=g) < 0.8).float()
+    X = to_split(K, x)
+    out = torch.zeros(b, c, device=DEV)
+    K.avgpool_dropout_fwd_split(X, b, hw, c, mask.to(DEV), 1.25, K.View(out))
+    ref = X.torch().cpu().view(b, hw, c).double().mean(1) * mask.double() * 1.25
+    close(out, ref, 1e-6, "avgpool split")

@@ -43,6 +43,33 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// ---- split-bf16: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significant bits) ----
+__device__ __forceinline__ uint32_t bf16_rn_bits(float x) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 h;\n\tcvt.rn.bf16.f32 h, %1;\n\tmov.b32 %0, {h, 0};\n\t}" : "=r"(r) : "f"(x));
+  return r;   // low 16 bits
+}
+__device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+  hi = bf16_rn_bits(x);
+  lo = bf16_rn_bits(x - __uint_as_float(hi << 16));
+}
+__device__ __forceinline__ float merge_bf16(uint32_t hi, uint32_t lo) {
+  return __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+}
+// 4 consecutive values -> 8 bytes per plane
+__device__ __forceinline__ void store4_split(uint16_t* hi, uint16_t* lo, const float v[4]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
+  *reinterpret_cast<uint2*>(hi) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+  *reinterpret_cast<uint2*>(lo) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+__device__ __forceinline__ void load4_split(const uint16_t* hi, const uint16_t* lo, float v[4]) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi), l = *reinterpret_cast<const uint2*>(lo);
+  v[0] = merge_bf16(h.x & 0xffffu, l.x & 0xffffu); v[1] = merge_bf16(h.x >> 16, l.x >> 16);
+  v[2] = merge_bf16(h.y & 0xffffu, l.y & 0xffffu); v[3] = merge_bf16(h.y >> 16, l.y >> 16);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1,0 +1,353 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM convolution on split-bf16 operands (ds_conv_bf16x3).
+//
+// Numerics: every fp32 operand value x is carried as two bf16 planes, x ~= hi + lo (hi = bf16(x), lo = bf16(x - hi),
+// 16 significant bits).  A product a*b is evaluated as  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  on the 5th-generation
+// tensor cores (kind::f16, fp32 accumulation in TMEM); the dropped a_lo*b_lo term is 2^-16 relative.  This keeps the
+// Inception tower's logits within ~2e-4 of the fp32 reference (one TF32 or bf16 pass is ~1e-2 after 22 layers) at
+// 1.5x the tensor time of a single TF32 pass.
+//
+// Structure (one CTA per SM, 192 threads, loops over 128 x BN output tiles):
+//   warp 0 / lane 0 : TMA producer.  Per K chunk (one filter tap x 64 channels) four tiles land 128B-swizzled and
+//                     K-major in a `stages`-deep ring: A_hi, A_lo (2-D tiled map for 1x1, im2col map for 3x3 - the TMA
+//                     unit walks the 128 pixels across rows / images and zero-fills the halo), B_hi, B_lo.
+//   warp 1 / lane 0 : MMA issuer.  3 x tcgen05.mma (M=128, N=BN, K=16) per 16 channels into one of two TMEM
+//                     accumulators (2 x 256 columns); tcgen05.commit releases ring slots and publishes the accumulator.
+//   warps 2-5       : epilogue, overlapped with the next tile's main loop.  TMEM -> registers (tcgen05.ld 32x32b.x32),
+//                     scale / bias / ReLU / accumulate, optional per-channel sum and sum-of-squares for batch-norm
+//                     (butterfly reduce + fp64 atomics), fp32 stores (plain or atomic for split-K).
+// Replaces the slim.conv2d sites of image_model/inception_v1.py:71-247, their input gradients (same contraction on
+// flipped weights), the weight gradients of Mixed_5c (:229-248, as pixel-major GEMMs with split-K) and the LSTM
+// products of image_text_model/im_text_rnn_model.py:89-90.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace {
+
+using namespace ds::ptx;
+
+constexpr int BM = 128;
+constexpr int KC = 64;                     // bf16 elements per K chunk = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * 128;     // 16 KB per plane
+constexpr int MAX_STAGES = 8;
+constexpr int ACC_COLS = 256;              // TMEM columns per accumulator buffer
+constexpr int THREADS = 192;
+
+struct Params {
+  int64_t M, N, ldc;
+  float* c;
+  const float* scale;
+  const float* bias;
+  double* stats;
+  int flags;
+  int bn;            // columns per tile (multiple of 16, <= 256)
+  int tiles_n;       // column tiles
+  int ksplit;        // K splits (grid-strided third tile dimension; epilogue adds atomically when > 1)
+  int64_t tiles;     // tiles_m * tiles_n * ksplit
+  int ksize;         // 1 or 3
+  int cin;
+  int cpt;           // K chunks per tap = ceil(cin / 64)
+  int iters;         // taps * cpt
+  int ipz;           // K iterations per split
+  int h, w, pad;
+  int stages;
+  int smem_stats;    // 1: batch-norm partial sums accumulate in shared memory (N <= 1024), 0: straight to global atomics
+};
+
+__device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t& m0, int& n0, int& it0, int& it1) {
+  const int z = (int)(t % p.ksplit);
+  const int64_t q = t / p.ksplit;
+  n0 = (int)(q % p.tiles_n) * p.bn;
+  m0 = (q / p.tiles_n) * BM;
+  it0 = z * p.ipz;
+  it1 = min(p.iters, it0 + p.ipz);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+  const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;   // 1024-aligned
+  // full[s] at bars + 8*s, empty[s] at bars + 64 + 8*s, tmem_full[b] at bars + 128 + 8*b, tmem_empty[b] at bars + 144 + 8*b,
+  // tmem base pointer at bars + 160
+  const uint32_t full0 = bars, empty0 = bars + 64, tfull0 = bars + 128, tempty0 = bars + 144, tmem_slot = bars + 160;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  // per-CTA batch-norm partial sums [2][N] (fp64), flushed with one global atomic per column when the CTA retires
+  double* sstats = reinterpret_cast<double*>(smem_raw + (bars + 256 - raw));
+  const bool do_stats = (p.flags & DS_EPI_STATS) != 0;
+  if (do_stats && p.smem_stats)
+    for (int i = threadIdx.x; i < 2 * (int)p.N; i += THREADS) sstats[i] = 0.0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 4);      // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * ACC_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t g = 0;      // global K-iteration counter (ring position)
+      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        int64_t m0; int n0, it0, it1;
+        tile_coords(p, t, m0, n0, it0, it1);
+        int img = 0, hp = 0, wq = 0;
+        if (p.ksize > 1) {
+          const int64_t hw = (int64_t)p.h * p.w;
+          img = (int)(m0 / hw);
+          const int rem = (int)(m0 - (int64_t)img * hw);
+          hp = rem / p.w;
+          wq = rem - hp * p.w;
+        }
+        for (int it = it0; it < it1; ++it, ++g) {
+          const int s = g % p.stages;
+          const uint32_t ph = (g / p.stages) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t fb = full0 + 8 * s;
+          mbar_expect_tx(fb, stage_bytes);
+          const int tap = it / p.cpt;
+          const int c0 = (it - tap * p.cpt) * KC;
+          const uint32_t sa = base + s * stage_bytes;
+          if (p.ksize == 1) {
+            tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
+            tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
+          } else {
+            const int r = tap / p.ksize, sx = tap - r * p.ksize;
+            tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+            tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+          }
+          const int kb = tap * p.cin + c0;
+          tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
+          tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.bn);
+      uint32_t g = 0, acc_it = 0;
+      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
+        int64_t m0; int n0, it0, it1;
+        tile_coords(p, t, m0, n0, it0, it1);
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        mbar_wait(tempty0 + 8 * buf, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * ACC_COLS;
+        for (int it = it0; it < it1; ++it, ++g) {
+          const int s = g % p.stages;
+          const uint32_t ph = (g / p.stages) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const int c0 = (it % p.cpt) * KC;
+          const int nk = (min(KC, p.cin - c0) + 15) >> 4;
+          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES, bh = al + A_TILE_BYTES, bl = bh + b_tile_bytes;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
+            const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
+            mma_f16(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
+            mma_f16(acc, dah, dbl, idesc, 1u);
+            mma_f16(acc, dah, dbh, idesc, 1u);
+          }
+          mma_commit(empty0 + 8 * s);
+        }
+        mma_commit(tfull0 + 8 * buf);
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5; warp w owns TMEM lanes 32*(w%4) .. +31) ----------------
+    const int quarter = warp & 3;
+    const bool atomic = p.ksplit > 1;
+    uint32_t acc_it = 0;
+    for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
+      int64_t m0; int n0, it0, it1;
+      tile_coords(p, t, m0, n0, it0, it1);
+      const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+      mbar_wait(tfull0 + 8 * buf, aph);
+      tc_fence_after();
+      const int64_t row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.c + row * p.ldc;
+      const uint32_t tbase = tmem_base + buf * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      const bool first_split = it0 == 0;
+      const int col_end = (int)min((int64_t)(n0 + p.bn), p.N);     // columns owned by this tile
+      for (int cb = 0; cb < p.bn; cb += 32) {
+        const int col0 = n0 + cb;
+        if (col0 >= col_end) break;                  // warp-uniform
+        float v[32];
+        tmem_ld32(tbase + (uint32_t)cb, v);
+        if (do_stats) {
+          // per-column sum and sum of squares over this warp's 32 rows: butterfly transpose-reduce, column j -> lane j
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = row_ok ? v[j] : 0.f;
+            s1[j] = x;
+            s2[j] = x * x;
+          }
+#pragma unroll
+          for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float send1 = hi ? s1[i] : s1[i + half];
+              const float keep1 = hi ? s1[i + half] : s1[i];
+              const float send2 = hi ? s2[i] : s2[i + half];
+              const float keep2 = hi ? s2[i + half] : s2[i];
+              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          // after the 5 rounds lane l holds column bitrev-free index: round with offset `off` keeps the upper half on
+          // lanes with that bit set, so lane l owns column l
+          const int col = col0 + lane;
+          if (col < col_end) {
+            double* dst = p.smem_stats ? sstats : p.stats;
+            atomicAdd(dst + col, (double)s1[0]);
+            atomicAdd(dst + p.N + col, (double)s2[0]);
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = col0 + j;
+            if (col < col_end) {                     // N, bn % 4 == 0 -> whole float4 valid
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.scale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+              }
+              if (p.bias && first_split) {
+                const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+              }
+              float4* dst = reinterpret_cast<float4*>(crow + col);
+              if (atomic) {
+                atomicAdd(crow + col, o.x); atomicAdd(crow + col + 1, o.y);
+                atomicAdd(crow + col + 2, o.z); atomicAdd(crow + col + 3, o.w);
+              } else {
+                if (p.flags & DS_EPI_ACCUMULATE) {
+                  const float4 q = *dst;
+                  o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                }
+                if (p.flags & DS_EPI_RELU) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                *dst = o;
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+    if (do_stats && p.smem_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+      for (int i = threadIdx.x - 64; i < 2 * (int)p.N; i += 128) {
+        const double v = sstats[i];
+        if (v != 0.0) atomicAdd(p.stats + i, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+int pick_bn(int64_t m, int64_t n, int sms) {
+  // fewest column tiles (each a multiple of 16, <= 256, as even as possible); when that leaves SMs idle (small-M
+  // products such as the LSTM step) split N further, down to 32-wide tiles
+  const int64_t tiles_m = (m + BM - 1) / BM;
+  int64_t tiles_n = (n + 255) / 256;
+  while (tiles_m * tiles_n < sms && (n + tiles_n) / (tiles_n + 1) >= 32) ++tiles_n;
+  int bn = (int)((n + tiles_n - 1) / tiles_n);
+  bn = (bn + 15) / 16 * 16;
+  return bn < 16 ? 16 : bn;
+}
+
+}  // namespace
+
+extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                              int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                              float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
+                              int ksplit, void* stream) {
+  DS_REQUIRE(ds::g_encode_tiled && ds::g_encode_im2col, "ds_init() has not been called");
+  DS_REQUIRE(ksize == 1 || ksize == 3, "ds_conv_bf16x3 supports 1x1 and 3x3 filters");
+  DS_REQUIRE((ksize == 1 || cin % 8 == 0) && n % 4 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "alignment (see deepsent.h)");
+  DS_REQUIRE((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)bt_hi | (uintptr_t)bt_lo | (uintptr_t)c) & 15) == 0, "16-byte aligned bases");
+  DS_REQUIRE(!(flags & DS_EPI_STATS) || stats != nullptr, "DS_EPI_STATS needs a stats buffer");
+  const int64_t M = batch * h * w;
+  if (M == 0 || n == 0) return 0;
+  const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
+  Params p;
+  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags;
+  p.bn = ds::g_debug[1] > 0 ? ds::g_debug[1] : pick_bn(M, n, sms);
+  p.tiles_n = (int)ds::cdiv(n, p.bn);
+  p.ksize = ksize; p.cin = (int)cin; p.cpt = (int)((cin + KC - 1) / KC);
+  p.iters = ksize * ksize * p.cpt;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > p.iters) ksplit = p.iters;
+  p.ipz = (int)ds::cdiv(p.iters, ksplit);
+  p.ksplit = (int)ds::cdiv(p.iters, p.ipz);
+  DS_REQUIRE(p.ksplit == 1 || !(flags & (DS_EPI_RELU | DS_EPI_STATS)), "split-K adds atomically: no ReLU / stats epilogue");
+  p.tiles = ds::cdiv(M, BM) * p.tiles_n * p.ksplit;
+  p.h = (int)h; p.w = (int)w; p.pad = (ksize - 1) / 2;
+  const int64_t ktot = (int64_t)ksize * ksize * cin;
+
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  int r = 0;
+  for (int plane = 0; plane < 2 && !r; ++plane) {
+    CUtensorMap* tm = plane ? &tmAl : &tmAh;
+    const uint16_t* ptr = plane ? a_lo : a_hi;
+    if (ksize == 1) r = ds::make_tmap_2d_bf16(tm, ptr, (uint64_t)M, (uint64_t)cin, (uint64_t)lda, KC, BM);
+    else r = ds::make_tmap_im2col_bf16(tm, ptr, (uint64_t)batch, (uint64_t)h, (uint64_t)w, (uint64_t)cin, (uint64_t)lda, ksize, p.pad, KC, BM);
+  }
+  if (r) return ds::fail("cuTensorMapEncode(A) failed: CUresult %d (M=%lld cin=%lld lda=%lld ks=%d)", r, (long long)M, (long long)cin, (long long)lda, ksize);
+  r = ds::make_tmap_2d_bf16(&tmBh, bt_hi, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)p.bn);
+  if (!r) r = ds::make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)p.bn);
+  if (r) return ds::fail("cuTensorMapEncode(B) failed: CUresult %d (n=%lld ktot=%lld ldb=%lld bn=%d)", r, (long long)n, (long long)ktot, (long long)ldb, p.bn);
+
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
+  p.smem_stats = ((flags & DS_EPI_STATS) && n <= 1024) ? 1 : 0;
+  const int stats_bytes = p.smem_stats ? (int)(2 * n * sizeof(double)) : 0;
+  int stages = (226 * 1024 - 1024 - 256 - stats_bytes) / stage_bytes;
+  if (ds::g_debug[2] > 0) stages = ds::g_debug[2];
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + stats_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;     // one CTA per SM: each CTA owns all 512 TMEM columns
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, sms);
+  conv_bf16x3_kernel<<<grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, p);
+  DS_LAUNCH_CHECK();
+  return 0;
+}

@@ -21,7 +21,7 @@ def _stream() -> int:
 def _p(t) -> int:
     if t is None:
         return 0
-    if isinstance(t, View):
+    if isinstance(t, (View, SView)):
         return t.ptr
     return t.data_ptr()
 
@@ -49,6 +49,42 @@ class View:
         return self.base.view(self.rows, self.ld)[:, self.coff:self.coff + self.cols]
 
 
+class SView:
+    """Split-bf16 activation window: logical [rows, cols] values stored as hi | lo bf16 planes.  `base` is a bf16 tensor whose
+    last dimension holds [hi(C) | lo(C)] per row (ld = 2*C elements, lo plane C elements after the hi plane)."""
+    __slots__ = ("base", "rows", "cols", "ld", "coff", "lo")
+
+    def __init__(self, base: torch.Tensor, cols: int = None, coff: int = 0, ld: int = None, lo: int = None):
+        assert base.dtype == torch.bfloat16 and base.is_contiguous()
+        self.base = base
+        self.ld = int(ld if ld is not None else base.shape[-1])
+        self.lo = int(lo if lo is not None else self.ld // 2)
+        self.rows = base.numel() // self.ld
+        self.coff = int(coff)
+        self.cols = int(cols if cols is not None else self.lo - coff)
+
+    @property
+    def ptr(self) -> int:            # hi plane
+        return self.base.data_ptr() + 2 * self.coff
+
+    @property
+    def lo_ptr(self) -> int:
+        return self.base.data_ptr() + 2 * (self.coff + self.lo)
+
+    def slice(self, coff: int, cols: int) -> "SView":
+        return SView(self.base, cols, self.coff + coff, self.ld, self.lo)
+
+    def torch(self) -> torch.Tensor:
+        """merged fp32 copy (debug / tests)"""
+        b = self.base.view(self.rows, self.ld)
+        return b[:, self.coff:self.coff + self.cols].float() + b[:, self.lo + self.coff:self.lo + self.coff + self.cols].float()
+
+
+def new_split(rows_shape, cols: int, device) -> torch.Tensor:
+    """zeroed split buffer for a logical [*rows_shape, cols] activation"""
+    return torch.zeros(*rows_shape, 2 * cols, dtype=torch.bfloat16, device=device)
+
+
 def init(device: int = 0):
     lib().init(device)
 
@@ -59,6 +95,57 @@ def conv_tc(a: View, batch, h, w, cin, ksize, bt, ldb, n, c: View, scale=None, b
         flags |= EPI_STATS
     lib().conv_tc(a.ptr, a.ld, batch, h, w, cin, ksize, _p(bt), ldb, n, c.ptr, c.ld, _p(scale), _p(bias), _p(stats), flags,
                   _stream())
+
+
+def conv_bf16x3(a: SView, batch, h, w, cin, ksize, bt: SView, n, c: View, scale=None, bias=None, stats=None, flags=0, ksplit=1):
+    """tcgen05 split-bf16 implicit GEMM; `bt` is the K-major weight operand [n, ksize*ksize*cin] as an SView"""
+    if stats is not None:
+        flags |= EPI_STATS
+    lib().conv_bf16x3(a.ptr, a.lo_ptr, a.ld, batch, h, w, cin, ksize, bt.ptr, bt.lo_ptr, bt.ld, n, c.ptr, c.ld, _p(scale), _p(bias),
+                      _p(stats), flags, ksplit, _stream())
+
+
+def gemm_bf16x3(a: SView, bt: SView, c: View, k=None, bias=None, flags=0, ksplit=1):
+    """C[rows, n] = A[rows, k] x Bt[n, k]^T on the tensor cores (split-bf16 operands)"""
+    conv_bf16x3(a, a.rows, 1, 1, k if k is not None else a.cols, 1, bt, bt.rows, c, None, bias, None, flags, ksplit)
+
+
+def split_bf16(x: View, out: SView):
+    lib().split_bf16(x.ptr, x.ld, x.rows, x.cols, out.ptr, out.lo_ptr, out.ld, _stream())
+
+
+def merge_bf16(x: SView, out: View):
+    lib().merge_bf16(x.ptr, x.lo_ptr, x.ld, x.rows, x.cols, out.ptr, out.ld, _stream())
+
+
+def im2col_transpose_split(x: SView, batch, h, w, cin, ksize, out: SView):
+    lib().im2col_transpose_split(x.ptr, x.lo_ptr, x.ld, batch, h, w, cin, ksize, out.ptr, out.lo_ptr, out.ld, _stream())
+
+
+def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None):
+    """dgrad: SView over the [cin, kh*kw*dgrad_tap] operand, already sliced to this conv's channel offset"""
+    kh, kw, cin, cout = hwio.shape
+    lib().repack_conv_weights_split(hwio.data_ptr(), kh, kw, cin, cout, fwd.ptr if fwd else 0, fwd.lo_ptr if fwd else 0,
+                                    fwd.ld if fwd else 0, dgrad.ptr if dgrad else 0, dgrad.lo_ptr if dgrad else 0,
+                                    dgrad.ld if dgrad else 0, dgrad_tap if dgrad_tap is not None else cout, _stream())
+
+
+def bn_apply_relu_split(z: View, mean, rstd, eps, beta, y: SView, flags=0):
+    lib().bn_apply_relu_split(z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), eps, _p(beta), y.ptr, y.lo_ptr, y.ld, flags, _stream())
+
+
+def bn_relu_bwd_apply_split(dy: View, z: View, mean, rstd, beta, sums, sums_ld, dz: SView, dbeta):
+    lib().bn_relu_bwd_apply_split(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
+                                  dz.ptr, dz.lo_ptr, dz.ld, _p(dbeta), _stream())
+
+
+def maxpool_fwd_split(x: SView, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, y: SView, argmax=None):
+    lib().maxpool_fwd_split(x.ptr, x.lo_ptr, x.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, y.ptr, y.lo_ptr, y.ld,
+                            _p(argmax), _stream())
+
+
+def avgpool_dropout_fwd_split(x: SView, batch, hw, c, mask, inv_keep, out: View):
+    lib().avgpool_dropout_fwd_split(x.ptr, x.lo_ptr, x.ld, batch, hw, c, _p(mask), inv_keep, out.ptr, out.ld, _stream())
 
 
 def gemm_tc(a: View, bt, ldb, n, c: View, k=None, bias=None, flags=0):
