@@ -92,6 +92,8 @@ int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, co
 int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
                                const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
+/* dbeta[c] = sums[c] (the frozen stem needs no dz: only its beta gradient) */
+int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream);
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,
                          int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo, uint16_t* y_hi, uint16_t* y_lo,
                          int64_t ldy, uint8_t* argmax, void* stream);
@@ -175,14 +177,15 @@ int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const in
                         int64_t steps, float* out, int64_t ldo, void* stream);
 /* one time step.  pre = zh + xw + bias, gate order i,j,f,o (BasicLSTMCell): c' = c*sig(f+fb)+sig(i)*tanh(j),
  * h' = tanh(c')*sig(o); rows with t >= seq_len carry (c,h) (dynamic_rnn semantics).  Saves the gate
- * activations [batch,4n] for BPTT. */
+ * activations [batch,4n] for BPTT.  h_hi/h_lo (optional, row stride ldh bf16 elements): split-bf16 copy of h_out, the operand
+ * of the next step's recurrent contraction. */
 int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const float* c_prev, const float* h_prev,
                       const int64_t* seq_len, int64_t t, int64_t batch, int64_t n, float forget_bias,
-                      float* gates, float* c_out, float* h_out, int round_tf32, void* stream);
-/* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n]; updates carries */
+                      float* gates, float* c_out, float* h_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ldh, void* stream);
+/* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n] (+ optional split-bf16 copy); updates carries */
 int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len,
                       int64_t t, int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc,
-                      float* dz, int round_tf32, void* stream);
+                      float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream);
 
 /* ---- head / loss / optimiser ------------------------------------------------------------ */
 /* slim.losses.softmax_cross_entropy (im_text_rnn_model.py:124-125): loss_rows[b], dlogits = (p - onehot)*scale */

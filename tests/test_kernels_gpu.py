@@ -287,12 +287,12 @@ def test_lstm_sequence_forward_backward(K):
     G = torch.zeros(t_, b, 4 * n, device=DEV); zh = torch.zeros(b, 4 * n, device=DEV)
     for t in range(t_):
         K.gemm_nn(K.View(H[t]), K.View(wh), K.View(zh))
-        K.lstm_gates_fwd(zh, xw[t * b:(t + 1) * b], bd, C[t], H[t], ld, t, b, n, 1.0, G[t], C[t + 1], H[t + 1], False)
+        K.lstm_gates_fwd(zh, xw[t * b:(t + 1) * b], bd, C[t], H[t], ld, t, b, n, 1.0, G[t], C[t + 1], H[t + 1], None)
     close(H[t_], last, 1e-5, "lstm last h")
     dhc = dlast.to(DEV).clone(); dc = torch.zeros(b, n, device=DEV); dhr = torch.zeros(b, n, device=DEV)
     DZ = torch.zeros(t_, b, 4 * n, device=DEV)
     for t in reversed(range(t_)):
-        K.lstm_gates_bwd(G[t], C[t], C[t + 1], ld, t, b, n, dhr if t < t_ - 1 else None, dhc, dc, DZ[t], False)
+        K.lstm_gates_bwd(G[t], C[t], C[t + 1], ld, t, b, n, dhr if t < t_ - 1 else None, dhc, dc, DZ[t], None)
         K.gemm_nt(K.View(DZ[t]), K.View(wh), K.View(dhr))
     dk = torch.zeros(e + n, 4 * n, device=DEV)
     K.gemm_tn(K.View(xd.view(t_ * b, e)), K.View(DZ.view(t_ * b, 4 * n)), K.View(dk[:e]))

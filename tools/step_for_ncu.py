@@ -17,7 +17,7 @@ from tumblr_emotions_b200.engine import Engine
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--model", default="joint")
-ap.add_argument("--precision", default="tf32")
+ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--forward-only", action="store_true")
 args = ap.parse_args()
 

@@ -6,7 +6,7 @@ Mirrors (same names, positional arguments, prints and files):
   image_model/im_model.py               : _CONFIG :20-25, ImageModel :139-164, train_image_model :166-225, get_init_fn :118-137
   text_model/text_embedding.py          : _CONFIG :16-24, TextModel :37-86, train_text_model :89-150
 The TF graph objects become eager objects: `.logits`, `.labels`, `.concat_features` are torch tensors refreshed by
-every step.  Extra config keys (never renamed ones): 'precision' ('tf32' | 'fp32'), 'synthetic' (bool), 'num_samples',
+every step.  Extra config keys (never renamed ones): 'precision' ('bf16x3' | 'fp32'), 'synthetic' (bool), 'num_samples',
 'num_classes', 'vocab_size', 'seed'.
 """
 from __future__ import annotations
@@ -136,7 +136,7 @@ class _Model:
         is_training = (mode == 'train')
         self.is_training = is_training
         kw = dict(model=self.kind, batch=int(config['batch_size']), nb_emotions=self.nb_emotions,
-                  precision=config.get('precision', 'tf32'), device=local, seed=int(config.get('seed', _RANDOM_SEED)),
+                  precision=config.get('precision', 'bf16x3'), device=local, seed=int(config.get('seed', _RANDOM_SEED)),
                   world_size=world, training=is_training, dropout="rng" if is_training else "none")
         if self.kind != "text":
             kw['final_endpoint'] = config['final_endpoint']

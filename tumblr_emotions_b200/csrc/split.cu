@@ -100,6 +100,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __
   }
 }
 
+__global__ void bn_dbeta_kernel(const double* __restrict__ sums, int n, float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dbeta[i] = (float)sums[i];
+}
+
 // ---- pooling on split activations ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
                                                                 int64_t ldx, int64_t B, int h, int w, int c4, int k, int stride,
@@ -279,6 +284,13 @@ int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, in
   if (m == 0 || n == 0) return 0;
   bn_bwd_apply_split_kernel<<<ew_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, (int)n, mean, rstd, beta, sums,
                                                                              sums_ld, dz_hi, dz_lo, lddz, dbeta);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream) {
+  if (n == 0) return 0;
+  bn_dbeta_kernel<<<(unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream)>>>(sums, (int)n, dbeta);
   DS_LAUNCH_CHECK();
   return 0;
 }

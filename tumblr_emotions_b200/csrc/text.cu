@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
                                                              const float* __restrict__ h_prev,
                                                              const int64_t* __restrict__ seq_len, int64_t t, int64_t B, int n,
                                                              float forget_bias, float* __restrict__ gates,
-                                                             float* __restrict__ c_out, float* __restrict__ h_out, int round_tf32) {
+                                                             float* __restrict__ c_out, float* __restrict__ h_out,
+                                                             uint16_t* __restrict__ h_hi, uint16_t* __restrict__ h_lo, int64_t ldh) {
   const int n4 = n >> 2;
   const int64_t total = B * n4;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -63,8 +64,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
       gf[k] = sigmoidf_(pre[2][k] + forget_bias);
       go[k] = sigmoidf_(pre[3][k]);
       const float c_new = cpv[k] * gf[k] + gi[k] * gj[k];
-      float h_new = tanhf(c_new) * go[k];
-      if (round_tf32) h_new = ds::to_tf32(h_new);
+      const float h_new = tanhf(c_new) * go[k];
       cn[k] = live ? c_new : cpv[k];
       hn[k] = live ? h_new : hpv[k];
     }
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
     *reinterpret_cast<float4*>(gates + gbase + 3 * n) = make_float4(go[0], go[1], go[2], go[3]);
     *reinterpret_cast<float4*>(c_out + b * n + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
     *reinterpret_cast<float4*>(h_out + b * n + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    if (h_hi) ds::store4_split(h_hi + b * ldh + u, h_lo + b * ldh + u, hn);
   }
 }
 
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
                                                              const float* __restrict__ c_cur,
                                                              const int64_t* __restrict__ seq_len, int64_t t, int64_t B, int n,
                                                              const float* __restrict__ dh_rec, float* __restrict__ dh_carry,
-                                                             float* __restrict__ dc, float* __restrict__ dz, int round_tf32) {
+                                                             float* __restrict__ dc, float* __restrict__ dz,
+                                                             uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo, int64_t lddz) {
   const int n4 = n >> 2;
   const int64_t total = B * n4;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -102,6 +104,11 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
       *reinterpret_cast<float4*>(dz + gbase + n) = zero;
       *reinterpret_cast<float4*>(dz + gbase + 2 * n) = zero;
       *reinterpret_cast<float4*>(dz + gbase + 3 * n) = zero;
+      if (dz_hi) {
+        const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ds::store4_split(dz_hi + b * lddz + g * n + u, dz_lo + b * lddz + g * n + u, z4);
+      }
       continue;
     }
     const float4 i4 = *reinterpret_cast<const float4*>(gates + gbase);
@@ -124,12 +131,17 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
       dj[k] = dct * gi[k] * (1.f - gj[k] * gj[k]);
       df[k] = dct * cp[k] * gf[k] * (1.f - gf[k]);
       dcp[k] = dct * gf[k];
-      if (round_tf32) { di[k] = ds::to_tf32(di[k]); dj[k] = ds::to_tf32(dj[k]); df[k] = ds::to_tf32(df[k]); dob[k] = ds::to_tf32(dob[k]); }
     }
     *reinterpret_cast<float4*>(dz + gbase) = make_float4(di[0], di[1], di[2], di[3]);
     *reinterpret_cast<float4*>(dz + gbase + n) = make_float4(dj[0], dj[1], dj[2], dj[3]);
     *reinterpret_cast<float4*>(dz + gbase + 2 * n) = make_float4(df[0], df[1], df[2], df[3]);
     *reinterpret_cast<float4*>(dz + gbase + 3 * n) = make_float4(dob[0], dob[1], dob[2], dob[3]);
+    if (dz_hi) {
+      ds::store4_split(dz_hi + b * lddz + u, dz_lo + b * lddz + u, di);
+      ds::store4_split(dz_hi + b * lddz + n + u, dz_lo + b * lddz + n + u, dj);
+      ds::store4_split(dz_hi + b * lddz + 2 * n + u, dz_lo + b * lddz + 2 * n + u, df);
+      ds::store4_split(dz_hi + b * lddz + 3 * n + u, dz_lo + b * lddz + 3 * n + u, dob);
+    }
     *reinterpret_cast<float4*>(dc + sb) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
     *reinterpret_cast<float4*>(dh_carry + sb) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -154,21 +166,21 @@ int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const in
 
 int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const float* c_prev, const float* h_prev,
                       const int64_t* seq_len, int64_t t, int64_t batch, int64_t n, float forget_bias, float* gates, float* c_out,
-                      float* h_out, int round_tf32, void* stream) {
+                      float* h_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ldh, void* stream) {
   DS_REQUIRE(n % 4 == 0, "hidden size must be a multiple of 4");
   if (batch * n == 0) return 0;
   lstm_gates_fwd_kernel<<<blocks_for(batch * (n / 4)), 256, 0, ds::S(stream)>>>(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, (int)n,
-                                                                             forget_bias, gates, c_out, h_out, round_tf32);
+                                                                             forget_bias, gates, c_out, h_out, h_hi, h_lo, ldh);
   DS_LAUNCH_CHECK();
   return 0;
 }
 
 int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len, int64_t t,
-                      int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc, float* dz, int round_tf32, void* stream) {
+                      int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc, float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream) {
   DS_REQUIRE(n % 4 == 0, "hidden size must be a multiple of 4");
   if (batch * n == 0) return 0;
   lstm_gates_bwd_kernel<<<blocks_for(batch * (n / 4)), 256, 0, ds::S(stream)>>>(gates, c_prev, c_cur, seq_len, t, batch, (int)n, dh_rec,
-                                                                             dh_carry, dc, dz, round_tf32);
+                                                                             dh_carry, dc, dz, dz_hi, dz_lo, lddz);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from .ops import View
+from .ops import SView, View
 from .topology import (BN_DECAY, BN_EPS, DROPOUT_KEEP, ENDPOINTS, FORGET_BIAS, IMAGE_SIZE, MIXED, SEQUENCE,
                        TRAINABLE_WEIGHT_PREFIXES, WEIGHT_DECAY, mixed_convs, same_pad)
 
@@ -42,17 +42,22 @@ def _align4(n: int) -> int:
 # ----------------------------------------------------------------------------------------------------------------
 class ConvUnit:
     """One contraction + train-mode BN + ReLU.  `scopes` has >1 entry for the fused sibling 1x1 convs of an inception
-    block (same input -> one GEMM with concatenated output channels)."""
+    block (same input -> one GEMM with concatenated output channels).
+
+    precision 'bf16x3': x / outs / dZ are split-bf16 windows (ops.SView) and the contraction runs on tcgen05
+    (ds_conv_bf16x3); the 7x7/2 stem reads the fp32 images with the SIMT kernel.  precision 'fp32': everything is fp32
+    (ops.View) on the SIMT kernels (cross-check build)."""
 
     def __init__(self, eng: "Engine", scopes: List[str], k: int, stride: int, cin: int, couts: List[int], h_in: int,
-                 x: View, outs: List[View], dx: Optional[View], douts: List[View], seg_cols: List[Tuple[int, int]],
+                 x, outs: List, dx: Optional[View], douts: List[View], seg_cols: List[Tuple[int, int]],
                  dx_accumulate: bool = False):
         self.eng, self.scopes, self.k, self.stride, self.cin, self.couts, self.h_in = eng, scopes, k, stride, cin, couts, h_in
         self.h_out, self.pad, _ = same_pad(h_in, k, stride)
         self.N = sum(couts)
         self.M = eng.batch * self.h_out * self.h_out
         self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
-        self.tc = eng.precision == "tf32" and stride == 1 and k in (1, 3) and cin % 8 == 0
+        self.split = eng.split
+        self.tc = self.split and stride == 1 and k in (1, 3) and cin % 8 == 0
         self.Z = eng.new(self.M, self.N)
         off = eng.bn_cursor
         eng.bn_cursor += self.N
@@ -65,8 +70,18 @@ class ConvUnit:
             c += n
         self.trainable = scopes[0].startswith(TRAINABLE_WEIGHT_PREFIXES)
         kk = k * k
-        self.w_fwd = eng.new(self.N, kk * cin) if self.tc else None          # [N][r][s][cin]
-        self.w_dgrad = eng.new(cin, kk * self.N)                              # [cin][r'][s'][N]
+        if self.tc:
+            self.w_fwd = SView(eng.new_split((self.N,), kk * cin))           # [N][r][s][cin]
+            self.w_dgrad = SView(eng.new_split((cin,), kk * self.N))         # [cin][r'][s'][N]
+        else:
+            self.w_fwd = None
+            self.w_dgrad = eng.new(cin, kk * self.N)                          # fp32 [cin][r'][s'][N]
+        if eng.training and (dx is not None or self.trainable):
+            eng.dz_elems = max(eng.dz_elems, self.M * self.N)
+        if eng.training and self.trainable and self.split:
+            ldm = (self.M + 7) // 8 * 8
+            eng.wg_a_elems = max(eng.wg_a_elems, kk * cin * ldm)
+            eng.wg_b_elems = max(eng.wg_b_elems, self.N * ldm)
 
     # -- operand copies ------------------------------------------------------------------------------------
     def refresh_operands(self):
@@ -74,9 +89,11 @@ class ConvUnit:
         kk = self.k * self.k
         for s, c, n in self.scope_cols:
             w = e.weight(s + "/weights")
-            fwd = self.w_fwd[c:c + n] if self.tc else None
-            ops.repack_conv_weights(w, fwd=fwd, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
-                                    round_tf32=self.tc)
+            if self.tc:
+                ops.repack_conv_weights_split(w, fwd=self.w_fwd.rows_slice(c, n), dgrad=self.w_dgrad.slice(c, n), dgrad_tap=self.N)
+            else:
+                ops.repack_conv_weights(w, fwd=None, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
+                                        round_tf32=False)
 
     def bind(self):
         e = self.eng
@@ -86,13 +103,18 @@ class ConvUnit:
         self.mean, self.rstd = e.bn_mean[o:o + n], e.bn_rstd[o:o + n]
         self.stats, self.sums = e.stats[2 * o:2 * o + 2 * n], e.sums[2 * o:2 * o + 2 * n]
 
+    def _apply(self, z, mean, rstd, beta, out, flags):
+        if self.split:
+            ops.bn_apply_relu_split(z, mean, rstd, BN_EPS, beta, out, flags)
+        else:
+            ops.bn_apply_relu(z, mean, rstd, BN_EPS, beta, out, flags)
+
     # -- forward -------------------------------------------------------------------------------------------
     def fwd(self, train: bool):
         e, B, h = self.eng, self.eng.batch, self.h_in
         Zv = View(self.Z)
         if self.tc:
-            ops.conv_tc(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.k * self.k * self.cin, self.N, Zv,
-                        stats=self.stats if train else None)
+            ops.conv_bf16x3(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.N, Zv, stats=self.stats if train else None)
         else:
             if len(self.scopes) == 1:
                 ops.conv_simt(self.x, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
@@ -101,16 +123,14 @@ class ConvUnit:
                 ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
             if train:
                 ops.colstats(Zv, self.stats)
-        flags = ops.BN_TF32 if e.precision == "tf32" else 0
         if train:
             ops.bn_finalize(self.stats, self.M, self.N, self.mov_mean, self.mov_var, 1.0 - BN_DECAY, BN_EPS, self.mean, self.rstd,
                             ops.BN_UNBIASED if e.unbiased_moving_var else 0)
             for (c, n), out in zip(self.segs, self.outs):
-                ops.bn_apply_relu(Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], BN_EPS, self.beta[c:c + n], out, flags)
+                self._apply(Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], out, 0)
         else:
             for (c, n), out in zip(self.segs, self.outs):
-                ops.bn_apply_relu(Zv.slice(c, n), self.mov_mean[c:c + n], self.mov_var[c:c + n], BN_EPS, self.beta[c:c + n], out,
-                                  flags | ops.BN_USE_VAR)
+                self._apply(Zv.slice(c, n), self.mov_mean[c:c + n], self.mov_var[c:c + n], self.beta[c:c + n], out, ops.BN_USE_VAR)
 
     # -- backward ------------------------------------------------------------------------------------------
     def bwd(self):
@@ -119,25 +139,54 @@ class ConvUnit:
         for (c, n), dy in zip(self.segs, self.douts):
             ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
                                    self.N)
-        flags = ops.BN_TF32 if (e.precision == "tf32" and self.dx is not None) else 0
-        for (c, n), dy in zip(self.segs, self.douts):
-            ops.bn_relu_bwd_apply(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
-                                  self.N, self.dbeta[c:c + n], flags)
+        if self.dx is None and not self.trainable:      # frozen stem: only its beta gradient is needed
+            ops.bn_dbeta(self.sums, self.N, self.dbeta)
+            return
+        if self.split:
+            dZ = SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
+            for (c, n), dy in zip(self.segs, self.douts):
+                ops.bn_relu_bwd_apply_split(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n],
+                                            self.sums[c:], self.N, dZ.slice(c, n), self.dbeta[c:c + n])
+        else:
+            dZ = Zv                                      # fp32 build: dz overwrites z in place
+            for (c, n), dy in zip(self.segs, self.douts):
+                ops.bn_relu_bwd_apply(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
+                                      self.N, self.dbeta[c:c + n], 0)
         if self.trainable:   # Conv2DBackpropFilter only where the reference trains weights (inception_v1.py:229-235)
-            for s, c, n in self.scope_cols:
-                ops.conv_wgrad_simt(self.x, B, self.h_in, self.h_in, self.cin, self.k, self.k, self.pad, self.pad, Zv.slice(c, n), n,
-                                    e.grad(s + "/weights"))
+            self._wgrad(dZ)
         if self.dx is not None:
             fl = ops.EPI_ACCUMULATE if self.dx_accumulate else 0
             if self.tc:
-                ops.conv_tc(Zv, B, h, h, self.N, self.k, self.w_dgrad, self.k * self.k * self.N, self.cin, self.dx, flags=fl)
+                ops.conv_bf16x3(dZ, B, h, h, self.N, self.k, self.w_dgrad, self.cin, self.dx, flags=fl)
             else:
-                ops.conv_simt(Zv, B, h, h, self.N, self.k, self.k, 1, self.pad, self.pad, h, h, self.w_dgrad, self.cin, self.dx,
+                ops.conv_simt(dZ, B, h, h, self.N, self.k, self.k, 1, self.pad, self.pad, h, h, self.w_dgrad, self.cin, self.dx,
                               flags=fl, swk=1, swn=self.k * self.k * self.N)
+
+    def _wgrad(self, dZ):
+        e, B = self.eng, self.eng.batch
+        if not self.tc:
+            for s, c, n in self.scope_cols:
+                ops.conv_wgrad_simt(self.x, B, self.h_in, self.h_in, self.cin, self.k, self.k, self.pad, self.pad, dZ.slice(c, n), n,
+                                    e.grad(s + "/weights"))
+            return
+        # dW[(r,s,ci), n] = sum_pixels X[pix + (r,s), ci] dZ[pix, n]: pixel-major operands, split-K tensor-core GEMM
+        kk, M = self.k * self.k, self.M
+        ldm = (M + 7) // 8 * 8
+        At = SView(e.wg_a[:kk * self.cin * 2 * ldm].view(kk * self.cin, 2 * ldm))
+        Bt = SView(e.wg_b[:self.N * 2 * ldm].view(self.N, 2 * ldm))
+        ops.im2col_transpose_split(self.x, B, self.h_in, self.h_in, self.cin, self.k, At)
+        ops.im2col_transpose_split(dZ, B, self.h_out, self.h_out, self.N, 1, Bt)
+        for s, c, n in self.scope_cols:
+            g = e.grad(s + "/weights")
+            g.zero_()
+            tiles = -(-kk * self.cin // 128) * -(-n // 256)
+            chunks = -(-M // 64)
+            ksplit = max(1, min(chunks, -(-2 * e.sm_count // tiles)))
+            ops.gemm_bf16x3(At, Bt.rows_slice(c, n), View(g.view(kk * self.cin, n)), k=M, ksplit=ksplit)
 
 
 class PoolNode:
-    def __init__(self, eng, k, stride, c, h_in, x: View, y: View, dx: View, dy: View, dx_accumulate=False):
+    def __init__(self, eng, k, stride, c, h_in, x, y, dx: View, dy: View, dx_accumulate=False):
         self.eng, self.k, self.stride, self.c, self.h_in = eng, k, stride, c, h_in
         self.h_out, self.pad, _ = same_pad(h_in, k, stride)
         self.x, self.y, self.dx, self.dy, self.dx_accumulate = x, y, dx, dy, dx_accumulate
@@ -145,8 +194,9 @@ class PoolNode:
 
     def fwd(self, train):
         B = self.eng.batch
-        ops.maxpool_fwd(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
-                        self.y, self.argmax if train else None)
+        f = ops.maxpool_fwd_split if self.eng.split else ops.maxpool_fwd
+        f(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out, self.y,
+          self.argmax if train else None)
 
     def bwd(self):
         B = self.eng.batch
@@ -162,12 +212,12 @@ class Engine:
 
     def __init__(self, model: str = "joint", batch: int = 64, nb_emotions: int = 15, im_features: int = 256,
                  rnn_size: int = 1024, fc_size: int = 512, vocab: int = 400001, emb_dim: int = 50, post_size: int = 50,
-                 precision: str = "tf32", device: int = 0, seed: int = 0, world_size: int = 1, dropout: str = "rng",
+                 precision: str = "bf16x3", device: int = 0, seed: int = 0, world_size: int = 1, dropout: str = "rng",
                  unbiased_moving_var: bool = False, final_endpoint: str = "Mixed_5c", training: bool = True):
         if model not in ("joint", "image", "text"):
             raise ValueError("unknown model %r" % model)
-        if precision not in ("tf32", "fp32"):
-            raise ValueError("precision must be 'tf32' (tcgen05) or 'fp32' (SIMT cross-check)")
+        if precision not in ("bf16x3", "fp32"):
+            raise ValueError("precision must be 'bf16x3' (tcgen05, split-bf16 operands) or 'fp32' (SIMT cross-check)")
         if final_endpoint not in ENDPOINTS:
             raise ValueError("Unknown final endpoint %s" % final_endpoint)      # image_model/inception_v1.py:251
         if final_endpoint != "Mixed_5c":
@@ -181,6 +231,10 @@ class Engine:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         ops.init(device)
+        from ._lib import lib
+        self.sm_count = lib().sm_count() or 148
+        self.split = precision == "bf16x3"
+        self.dz_elems = self.wg_a_elems = self.wg_b_elems = 0
         self.seed = seed
         self.has_image, self.has_text = model in ("joint", "image"), model in ("joint", "text")
         self.tower_classes = im_features if model == "joint" else nb_emotions
@@ -202,6 +256,10 @@ class Engine:
         # ---- graph construction (allocates activations / gradients, records the parameter table) ----
         if self.has_image:
             self._build_tower()
+            if self.training and self.split:     # shared scratch: dZ of the unit being differentiated, wgrad operands
+                self.dz_scratch = self.new_split((self.dz_elems,), 1).view(-1)
+                self.wg_a = self.new_split((self.wg_a_elems,), 1).view(-1)
+                self.wg_b = self.new_split((self.wg_b_elems,), 1).view(-1)
         self._layout_params()
         for u in self.units:
             u.bind()
@@ -216,10 +274,24 @@ class Engine:
         self._bytes += t.numel() * t.element_size()
         return t
 
+    def new_split(self, rows_shape, cols: int):
+        """zeroed split-bf16 buffer for a logical fp32 [*rows_shape, cols] tensor (hi | lo planes per row)"""
+        t = ops.new_split(rows_shape, cols, self.device)
+        self._bytes += t.numel() * t.element_size()
+        return t
+
+    def act(self, *shape):
+        """activation buffer + window in the engine's operand format"""
+        if self.split:
+            t = self.new_split(shape[:-1], shape[-1])
+            return t, SView(t)
+        t = self.new(*shape)
+        return t, View(t)
+
     # -- tower construction -----------------------------------------------------------------------------------
     def _build_tower(self):
         B, tr = self.batch, self.training
-        act = View(self.images)
+        act = View(self.images)          # the stem reads the fp32 images
         dact = None                      # no gradient w.r.t. the images
         c, h = 3, IMAGE_SIZE
         for item in SEQUENCE:
@@ -227,28 +299,27 @@ class Engine:
             if kind == "conv":
                 _, _, k, s, cout = item
                 ho = same_pad(h, k, s)[0]
-                out = self.new(B, ho, ho, cout)
+                _, vout = self.act(B, ho, ho, cout)
                 dout = self.new(B, ho, ho, cout) if tr else None
-                u = ConvUnit(self, ["InceptionV1/" + name], k, s, c, [cout], h, act, [View(out)], dact,
+                u = ConvUnit(self, ["InceptionV1/" + name], k, s, c, [cout], h, act, [vout], dact,
                              [View(dout)] if tr else [None], [(0, cout)])
                 self.units.append(u); self.nodes.append(u)
-                act, dact, c, h = View(out), View(dout) if tr else None, cout, ho
+                act, dact, c, h = vout, View(dout) if tr else None, cout, ho
             elif kind == "maxpool":
                 _, _, k, s = item
                 ho = same_pad(h, k, s)[0]
-                out = self.new(B, ho, ho, c)
+                _, vout = self.act(B, ho, ho, c)
                 dout = self.new(B, ho, ho, c) if tr else None
-                self.nodes.append(PoolNode(self, k, s, c, h, act, View(out), dact, View(dout) if tr else None))
-                act, dact, h = View(out), View(dout) if tr else None, ho
+                self.nodes.append(PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None))
+                act, dact, h = vout, View(dout) if tr else None, ho
             else:
                 c0, c1a, c1b, c2a, c2b, c3, _ = MIXED[name]
                 convs = mixed_convs(name, c)
                 ctot = c0 + c1b + c2b + c3
-                OUT, T, P = self.new(B, h, h, ctot), self.new(B, h, h, c1a + c2a), self.new(B, h, h, c)
+                (_, vO), (_, vT), (_, vP) = self.act(B, h, h, ctot), self.act(B, h, h, c1a + c2a), self.act(B, h, h, c)
                 dOUT = self.new(B, h, h, ctot) if tr else None
                 dT = self.new(B, h, h, c1a + c2a) if tr else None
                 dP = self.new(B, h, h, c) if tr else None
-                vO, vT, vP = View(OUT), View(T), View(P)
                 g = (lambda t, *a: View(t).slice(*a) if a else View(t)) if tr else (lambda t, *a: None)
                 # fused sibling 1x1s (Branch_0, Branch_1 reduce, Branch_2 reduce) - inception_v1.py:85-91 pattern
                 u1 = ConvUnit(self, [convs[0][0], convs[1][0], convs[3][0]], 1, 1, c, [c0, c1a, c2a], h, act,
@@ -441,13 +512,14 @@ class Engine:
                 for k, t in self.frozen.items():
                     if k.endswith("/weights"):
                         ops.sumsq(t, 0.5 * WEIGHT_DECAY, self.loss_buf[3:4], accumulate=True)
-        if self.has_text and self.precision == "tf32":
+        if self.has_text and self.split:
             kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
-            wh = kern[self.emb_dim:]
-            ops.transpose(View(wh), View(self.whT))           # [4n, n]: forward operand (K-major)
-            ops.round_tf32(self.whT)
-            self.wh_r.copy_(wh)                               # [n, 4n]: BPTT operand
-            ops.round_tf32(self.wh_r)
+            e, n = self.emb_dim, self.rnn_size
+            ops.transpose(View(kern[e:]), View(self._whT32))                 # [4n, n]
+            ops.split_bf16(View(self._whT32), self.whT)                      # forward operand (K-major over h)
+            ops.split_bf16(View(kern[e:]), self.wh)                          # BPTT operand [n, 4n] (K-major over the gates)
+            ops.transpose(View(kern[:e]), View(self._wxT32, e, 0))           # [4n, 50] inside a zero-padded [4n, 64]
+            ops.split_bf16(View(self._wxT32), self.wxT)
 
     # -- text tower (im_text_rnn_model.py:80-92 / text_embedding.py:72-82) -------------------------------------
     def _build_text(self):
@@ -458,46 +530,73 @@ class Engine:
         self.G = self.new(T, B, 4 * n) if tr else self.new(1, B, 4 * n)
         self.ZH = self.new(B, 4 * n)
         self.text_feat = View(self.H[T])
-        if self.precision == "tf32":
-            self.whT, self.wh_r = self.new(4 * n, n), self.new(n, 4 * n)
+        if self.split:
+            self.Es = SView(self.new_split((T * B,), EMB_LD))
+            self.Hs = self.new_split((T + 1, B), n)                          # split copy of every h_t (GEMM operand)
+            self._whT32, self._wxT32 = self.new(4 * n, n), self.new(4 * n, EMB_LD)
+            self.whT, self.wh, self.wxT = SView(self.new_split((4 * n,), n)), SView(self.new_split((n,), 4 * n)), \
+                SView(self.new_split((4 * n,), EMB_LD))
         if tr:
             self.DZ = self.new(T * B, 4 * n)
             self.dh_carry, self.dc, self.dh_rec = self.new(B, n), self.new(B, n), self.new(B, n)
+            if self.split:
+                ld = (T * B + 7) // 8 * 8
+                self.DZs = self.new_split((T, B), 4 * n)
+                self.HsT = SView(self.new_split((n,), ld))                   # pixel... time-major operands of the weight gradients
+                self.DZsT = SView(self.new_split((4 * n,), ld))
+                self.EsT = SView(self.new_split((self.emb_dim,), ld))
 
     def text_fwd(self, train: bool):
         B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
-        tc = self.precision == "tf32"
         kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
         bias = self.weight("Text/rnn/basic_lstm_cell/bias")
         ops.embedding_gather(self.frozen["Text/W_embedding"], self.ids, View(self.E))
-        # input projection for all time steps at once (exact fp32: keeps the gathered rows bit-exact operands)
-        ops.gemm_nn(View(self.E, e), View(kern[:e]), View(self.XW))
+        # input projection for all time steps at once
+        if self.split:
+            ops.split_bf16(View(self.E), self.Es)
+            ops.gemm_bf16x3(self.Es, self.wxT, View(self.XW))
+        else:
+            ops.gemm_nn(View(self.E, e), View(kern[:e]), View(self.XW))
         for t in range(T):
-            if tc:
-                ops.gemm_tc(View(self.H[t]), self.whT, n, 4 * n, View(self.ZH))
+            if self.split:
+                ops.gemm_bf16x3(SView(self.Hs[t]), self.whT, View(self.ZH))
+                hs = SView(self.Hs[t + 1])
             else:
                 ops.gemm_nn(View(self.H[t]), View(kern[e:]), View(self.ZH))
+                hs = None
             ops.lstm_gates_fwd(self.ZH, self.XW[t * B:(t + 1) * B], bias, self.C[t], self.H[t], self.seq_lens, t, B, n, FORGET_BIAS,
-                               self.G[t if train else 0], self.C[t + 1], self.H[t + 1], tc)
+                               self.G[t if train else 0], self.C[t + 1], self.H[t + 1], hs)
 
     def text_bwd(self, dlast: View):
         B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
-        tc = self.precision == "tf32"
         kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
         ops.copy2d(dlast, View(self.dh_carry))
         self.dc.zero_()
         for t in reversed(range(T)):
+            dzs = SView(self.DZs[t]) if self.split else None
             ops.lstm_gates_bwd(self.G[t], self.C[t], self.C[t + 1], self.seq_lens, t, B, n, self.dh_rec if t < T - 1 else None,
-                               self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], tc)
+                               self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], dzs)
             if t > 0:
-                dz = View(self.DZ[t * B:(t + 1) * B])
-                if tc:
-                    ops.gemm_tc(dz, self.wh_r, 4 * n, n, View(self.dh_rec))
+                if self.split:
+                    ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec))
                 else:
-                    ops.gemm_nt(dz, View(kern[e:]), View(self.dh_rec))
+                    ops.gemm_nt(View(self.DZ[t * B:(t + 1) * B]), View(kern[e:]), View(self.dh_rec))
         dk = self.grad("Text/rnn/basic_lstm_cell/kernel")
-        ops.gemm_tn(View(self.E, e), View(self.DZ), View(dk[:e]))
-        ops.gemm_tn(View(self.H[:T].view(T * B, n)), View(self.DZ), View(dk[e:]))
+        if self.split:
+            # dW = [E | H]^T dZ over all T*B rows: time-major (K-major) operands + split-K tensor-core GEMMs
+            TB = T * B
+            ops.im2col_transpose_split(SView(self.DZs), TB, 1, 1, 4 * n, 1, self.DZsT)
+            ops.im2col_transpose_split(SView(self.Hs[:T]), TB, 1, 1, n, 1, self.HsT)
+            ops.im2col_transpose_split(self.Es, TB, 1, 1, e, 1, self.EsT)
+            dk.zero_()
+            chunks = -(-TB // 64)
+            ks = max(1, min(chunks, -(-2 * self.sm_count // (-(-n // 128) * -(-4 * n // 256)))))
+            ops.gemm_bf16x3(self.HsT, self.DZsT, View(dk[e:]), k=TB, ksplit=ks)
+            ks = max(1, min(chunks, -(-2 * self.sm_count // -(-4 * n // 256))))
+            ops.gemm_bf16x3(self.EsT, self.DZsT, View(dk[:e]), k=TB, ksplit=ks)
+        else:
+            ops.gemm_tn(View(self.E, e), View(self.DZ), View(dk[:e]))
+            ops.gemm_tn(View(self.H[:T].view(T * B, n)), View(self.DZ), View(dk[e:]))
         ops.colsum(View(self.DZ), self.grad("Text/rnn/basic_lstm_cell/bias"))
 
     # -- head ------------------------------------------------------------------------------------------------
@@ -530,7 +629,8 @@ class Engine:
                     ops.dropout_mask(self.drop_mask, DROPOUT_KEEP, self.seed + 0x5EED, self.drop_counter)
                 mask = self.drop_mask
             hw = self.tower_h * self.tower_h
-            ops.avgpool_dropout_fwd(self.tower_out, B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, View(self.feat))
+            (ops.avgpool_dropout_fwd_split if self.split else ops.avgpool_dropout_fwd)(
+                self.tower_out, B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, View(self.feat))
             wl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/weights").view(self.tower_c, self.tower_classes)
             bl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/biases")
             dst = View(self.concat, self.im_features, 0) if self.model == "joint" else self.logits_view()

@@ -74,6 +74,11 @@ class SView:
     def slice(self, coff: int, cols: int) -> "SView":
         return SView(self.base, cols, self.coff + coff, self.ld, self.lo)
 
+    def rows_slice(self, r0: int, nrows: int) -> "SView":
+        """rows [r0, r0+nrows) as a new window (same planes)"""
+        flat = self.base.view(-1, self.ld)
+        return SView(flat[r0:r0 + nrows], self.cols, self.coff, self.ld, self.lo)
+
     def torch(self) -> torch.Tensor:
         """merged fp32 copy (debug / tests)"""
         b = self.base.view(self.rows, self.ld)
@@ -128,6 +133,10 @@ def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SVie
     lib().repack_conv_weights_split(hwio.data_ptr(), kh, kw, cin, cout, fwd.ptr if fwd else 0, fwd.lo_ptr if fwd else 0,
                                     fwd.ld if fwd else 0, dgrad.ptr if dgrad else 0, dgrad.lo_ptr if dgrad else 0,
                                     dgrad.ld if dgrad else 0, dgrad_tap if dgrad_tap is not None else cout, _stream())
+
+
+def bn_dbeta(sums, n, dbeta):
+    lib().bn_dbeta(_p(sums), n, _p(dbeta), _stream())
 
 
 def bn_apply_relu_split(z: View, mean, rstd, eps, beta, y: SView, flags=0):
@@ -248,14 +257,16 @@ def embedding_gather(table: torch.Tensor, ids: torch.Tensor, out: View):
     lib().embedding_gather(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), b, t, out.ptr, out.ld, _stream())
 
 
-def lstm_gates_fwd(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, n, forget_bias, gates, c_out, h_out, round_tf32):
+def lstm_gates_fwd(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, n, forget_bias, gates, c_out, h_out, h_split: SView = None):
     lib().lstm_gates_fwd(_p(zh), _p(xw), _p(bias), _p(c_prev), _p(h_prev), _p(seq_len), t, batch, n, forget_bias, _p(gates),
-                         _p(c_out), _p(h_out), 1 if round_tf32 else 0, _stream())
+                         _p(c_out), _p(h_out), h_split.ptr if h_split else 0, h_split.lo_ptr if h_split else 0,
+                         h_split.ld if h_split else 0, _stream())
 
 
-def lstm_gates_bwd(gates, c_prev, c_cur, seq_len, t, batch, n, dh_rec, dh_carry, dc, dz, round_tf32):
+def lstm_gates_bwd(gates, c_prev, c_cur, seq_len, t, batch, n, dh_rec, dh_carry, dc, dz, dz_split: SView = None):
     lib().lstm_gates_bwd(_p(gates), _p(c_prev), _p(c_cur), _p(seq_len), t, batch, n, _p(dh_rec), _p(dh_carry), _p(dc), _p(dz),
-                         1 if round_tf32 else 0, _stream())
+                         dz_split.ptr if dz_split else 0, dz_split.lo_ptr if dz_split else 0, dz_split.ld if dz_split else 0,
+                         _stream())
 
 
 # ---- head / loss / optimiser ---------------------------------------------------------------------
