@@ -174,3 +174,33 @@ def test_graph_replay_equals_eager():
     d = (eng2.params - eng.params).abs()
     assert float(d.max()) <= 2.1 * 2 * 1e-3 and float(d.mean()) <= 2e-6, (float(d.max()), float(d.mean()))
     assert abs(eng2.total_loss() - eng.total_loss()) <= 1e-4 * abs(eng.total_loss())
+
+
+@pytest.mark.parametrize("model", ["joint", "image", "text"])
+def test_against_committed_golden_vectors(model):
+    """tests/golden/deepsent_golden.json (oracle float64 outputs, generated by tests/golden/make_golden.py): the CUDA step is
+    checked against the committed fixture without running the oracle."""
+    import json
+    import os
+    from tumblr_emotions_b200.engine import Engine
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deepsent_golden.json")))
+    g, vocab, batch = gold["cases"][model], gold["vocab"], gold["batch"]
+    eng = Engine(model=model, batch=batch, precision="bf16x3", vocab=vocab, dropout="given" if model != "text" else "none")
+    eng.load_state_dict(O.init_params(gold["param_seed"], model, vocab=vocab))          # initialiser only (no arithmetic)
+    bd = O.synthetic_batch(batch, seed=gold["batch_seed"], vocab=vocab, with_images=(model != "text"))
+    eng.set_batch(bd.get("images"), bd.get("ids") if model != "image" else None, bd.get("seq_lens") if model != "image" else None,
+                  bd["labels"])
+    if model != "text":
+        gen = torch.Generator().manual_seed(gold["mask_seed"])
+        eng.drop_mask.copy_((torch.rand(batch, 1024, generator=gen) < 0.8).float())
+    if model == "joint":
+        eng.forward(train=False)
+        torch.cuda.synchronize()
+        assert row_rel_l2(eng.get_logits(), torch.tensor(g["inference_logits"])) <= 1e-3
+    eng.train_step(gold["lr"])
+    torch.cuda.synchronize()
+    assert row_rel_l2(eng.get_logits(), torch.tensor(g["train_logits"])) <= 1e-3
+    assert abs(eng.total_loss() - g["train_loss"]) <= 1e-3 * abs(g["train_loss"])
+    for name, ref in g["grad_l2"].items():
+        got = float(eng.tensor(name, "grads").double().norm())
+        assert abs(got - ref) <= 0.05 * ref + 1e-12, (name, got, ref)

@@ -1,0 +1,239 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol of include/deepsent.h, the oracle reproduces
+the committed golden vectors, and the host logic around the kernels (TFRecord framing, synthetic split, checkpoints,
+call-surface shims, world_size-2 sharding/gather over gloo)."""
+import json
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import tf_semantics as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "deepsent_golden.json")))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from tumblr_emotions_b200.build import build
+    from tumblr_emotions_b200._lib import DeepSentLib, parse_header
+    path = build()
+    protos = parse_header()
+    assert len(protos) >= 45 and "ds_conv_bf16x3" in protos and "ds_last_error" in protos
+    lib = DeepSentLib(path)                 # getattr() on every prototype: a missing export raises AttributeError
+    assert lib.version() >= 100
+    # the error channel works without a device: a failed precondition returns non-zero and sets the message
+    with pytest.raises(RuntimeError, match="ds_init"):
+        lib.conv_bf16x3(0, 0, 8, 1, 1, 1, 8, 1, 0, 0, 8, 4, 0, 4, 0, 0, 0, 0, 1, 0)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from tumblr_emotions_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(model="text", batch=2, vocab=11)
+
+
+def test_product_code_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "tumblr_emotions_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", ""), f
+    for shim in ("image_text_model/im_text_rnn_model.py", "image_model/im_model.py", "text_model/text_embedding.py"):
+        assert "oracle" not in open(os.path.join(ROOT, shim)).read()
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+def _to64(d):
+    return {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("model", ["joint", "image", "text"])
+def test_oracle_reproduces_golden(model):
+    g = GOLD["cases"][model]
+    vocab, batch = GOLD["vocab"], GOLD["batch"]
+    p = _to64(O.init_params(GOLD["param_seed"], model, vocab=vocab))
+    bd = _to64(O.synthetic_batch(batch, seed=GOLD["batch_seed"], vocab=vocab, with_images=(model != "text")))
+    mask = None
+    if model != "text":
+        gen = torch.Generator().manual_seed(GOLD["mask_seed"])
+        mask = (torch.rand(batch, 1024, generator=gen) < 0.8).double().view(batch, 1, 1, 1024)
+    if model == "joint":
+        with torch.no_grad():
+            li, concat = O.deep_sentiment_forward(bd["images"], bd["ids"], bd["seq_lens"], p, is_training=False)
+        np.testing.assert_allclose(li.numpy(), np.array(g["inference_logits"]), rtol=1e-7, atol=1e-9)
+        assert abs(float(concat.norm()) - g["inference_concat_l2"]) <= 1e-8 * g["inference_concat_l2"]
+    opt = O.TFAdam(O.trainable_names(p), p)
+    loss, logits, grads = O.train_step(model, p, opt, GOLD["lr"], bd, mask)
+    np.testing.assert_allclose(logits.detach().numpy(), np.array(g["train_logits"]), rtol=1e-7, atol=1e-9)
+    assert abs(float(loss) - g["train_loss"]) <= 1e-9 * abs(g["train_loss"])
+    for k, v in g["grad_l2"].items():
+        assert abs(float(grads[k].double().norm()) - v) <= 1e-6 * v + 1e-14, k
+
+
+# ------------------------------------------------------------------------------------------------ TFRecord / data
+def test_crc32c_known_answers():
+    from tumblr_emotions_b200.tfrecord import crc32c, masked_crc
+    assert crc32c(b"123456789") == 0xE3069283           # RFC 3720 check value
+    assert crc32c(b"") == 0
+    assert crc32c(bytes(32)) == 0x8A9136AA              # RFC 3720 B.4: 32 zero bytes
+    m = masked_crc(b"123456789")
+    assert m == ((((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF)
+
+
+def test_tfrecord_roundtrip_and_corruption(tmp_path):
+    from tumblr_emotions_b200 import tfrecord as T
+    ex = {'text': np.arange(50, dtype=np.int64) * 7919, 'seq_len': 13, 'image/class/label': 4, 'post_id': 2 ** 40 + 5, 'day': 6,
+          'image/encoded': b'\xff\xd8jpegbytes', 'image/format': b'jpg'}
+    payload = T.encode_example(ex)
+    back = T.decode_example(payload)
+    assert list(back['text']) == list(ex['text']) and back['seq_len'] == [13] and back['post_id'] == [2 ** 40 + 5]
+    assert back['image/encoded'] == ex['image/encoded']
+    path = str(tmp_path / "a.tfrecord")
+    assert T.write_records(path, [payload, b"", payload]) == 3
+    assert list(T.read_records(path)) == [payload, b"", payload]
+    raw = bytearray(open(path, 'rb').read())
+    raw[20] ^= 0x01
+    open(path, 'wb').write(raw)
+    with pytest.raises(IOError):
+        list(T.read_records(path))
+
+
+def test_synthetic_tfrecord_split_config1(tmp_path):
+    """BASELINE config 1: 1k synthetic (token_ids, label) records, 15 classes, 5 shards, batch 32"""
+    from tumblr_emotions_b200 import tfrecord as T
+    from tumblr_emotions_b200.data import open_split
+    d = str(tmp_path)
+    T.write_synthetic_dataset(d, num_train=1000, num_valid=50, vocab_size=400001)
+    assert len(T.split_files("train", d)) == 5
+    ds = open_split("train", d, {}, with_images=False)
+    assert ds.num_samples == 1000 and ds.num_classes == 15
+    b = ds.next_batch(32)
+    assert b["ids"].shape == (32, 50) and b["ids"].dtype == torch.int64 and b["seq_lens"].dtype == torch.int64
+    pos = torch.arange(50).unsqueeze(0)
+    assert bool(((b["ids"] == 400000) == (pos >= b["seq_lens"].unsqueeze(1))).all())       # <ukn> padding past seq_len
+    assert int(b["labels"].min()) >= 0 and int(b["labels"].max()) < 15
+    # two ranks see disjoint records
+    r0 = open_split("train", d, {}, rank=0, world=2, with_images=False).next_batch(16)["post_ids"]
+    r1 = open_split("train", d, {}, rank=1, world=2, with_images=False).next_batch(16)["post_ids"]
+    assert not set(r0.tolist()) & set(r1.tolist())
+    with pytest.raises(ValueError):
+        open_split("test", d, {})
+
+
+def test_synthetic_posts_follow_the_record_schema():
+    from tumblr_emotions_b200.data import SyntheticPosts
+    ds = SyntheticPosts(num_samples=64, vocab_size=1001, with_images=True, image_size=32)
+    b = ds.next_batch(8)
+    assert b["images"].shape == (8, 32, 32, 3) and b["images"].dtype == torch.float32
+    assert float(b["images"].min()) >= -1.0 and float(b["images"].max()) <= 1.0
+    assert int(b["seq_lens"].min()) >= 1 and int(b["seq_lens"].max()) <= 50
+    pos = torch.arange(50).unsqueeze(0)
+    assert bool(((b["ids"] == 1000) == (pos >= b["seq_lens"].unsqueeze(1))).all())
+    assert float(ds.embedding[-1].abs().max()) == 0.0 and ds.embedding.shape == (1001, 50)
+
+
+# ------------------------------------------------------------------------------------------------ call surface
+def test_call_surface_shims_match_reference_names():
+    sys.path.insert(0, ROOT)
+    from image_model import im_model
+    from image_text_model import im_text_rnn_model
+    from text_model import text_embedding
+    # reference defaults: im_text_rnn_model.py:24-35, im_model.py:20-25, text_embedding.py:16-24
+    assert im_text_rnn_model._CONFIG == {'mode': 'train', 'dataset_dir': 'data', 'text_dir': 'text_model', 'emb_dir': 'embedding_weights',
+                                         'filename': 'glove.6B.50d.txt', 'initial_lr': 1e-3, 'decay_factor': 0.3, 'batch_size': 64,
+                                         'im_features_size': 256, 'rnn_size': 1024, 'final_endpoint': 'Mixed_5c', 'fc_size': 512}
+    assert im_model._CONFIG['batch_size'] == 64 and im_model._CONFIG['final_endpoint'] == 'Mixed_5c'
+    assert text_embedding._CONFIG['rnn_size'] == 1024 and text_embedding._POST_SIZE == 50
+    import inspect
+    assert list(inspect.signature(im_text_rnn_model.train_deep_sentiment).parameters)[:3] == ['checkpoints_dir', 'train_dir', 'num_steps']
+    assert list(inspect.signature(im_model.train_image_model).parameters)[:3] == ['checkpoints_dir', 'train_dir', 'num_steps']
+    assert list(inspect.signature(text_embedding.train_text_model).parameters)[:2] == ['train_dir', 'num_steps']
+    assert list(inspect.signature(im_text_rnn_model.correlation_matrix).parameters)[:2] == ['nb_batches', 'checkpoint_dir']
+
+
+def test_latest_checkpoint_lookup(tmp_path):
+    from tumblr_emotions_b200.api import latest_checkpoint
+    d = str(tmp_path)
+    assert latest_checkpoint(d) is None
+    for step in (5, 20, 100):
+        np.savez(os.path.join(d, "model.ckpt-%d.npz" % step), global_step=np.asarray(step))
+    assert latest_checkpoint(d).endswith("model.ckpt-100.npz")          # numeric, not lexicographic, order
+    with open(os.path.join(d, "checkpoint"), "w") as f:
+        f.write('model_checkpoint_path: "model.ckpt-20.npz"\n')
+    assert latest_checkpoint(d).endswith("model.ckpt-20.npz")
+
+
+def test_topology_matches_oracle_table():
+    from tumblr_emotions_b200 import topology as Tp
+    assert Tp.conv_specs() == O.conv_specs()
+    assert Tp.same_pad(224, 7, 2) == O.tf_same_pad(224, 7, 2) == (112, 2, 3)
+
+
+# ------------------------------------------------------------------------------------------------ world_size 2 over gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tumblr_emotions_b200.api import gather_in_batch_order, make_allreduce
+        # (1) feature-extraction sharding: batch i lives on rank i % world; the gather restores single-process order
+        nb_batches, bs, classes = 5, 4, 15
+        full_l = torch.arange(nb_batches * bs * classes, dtype=torch.float32).view(nb_batches, bs, classes)
+        full_y = torch.arange(nb_batches * bs, dtype=torch.int64).view(nb_batches, bs)
+        mine = [i for i in range(nb_batches) if i % world == rank]
+        l, y = gather_in_batch_order(full_l[mine].reshape(-1, classes), full_y[mine].reshape(-1), nb_batches, bs, world)
+        ok1 = torch.equal(l, full_l.view(-1, classes)) and torch.equal(y, full_y.view(-1))
+        # (2) flat gradient all-reduce: sum over ranks, 1/world folded in afterwards == model_deploy's mean of clone gradients
+        g = torch.full((1000,), float(rank + 1))
+        make_allreduce(world)(g)
+        ok2 = bool((g / world == (1 + 2) / 2.0).all())
+        q.put((rank, ok1, ok2))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding_and_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res), res
+
+
+def test_two_clone_gradient_mean_equals_full_batch_without_bn():
+    """model_deploy semantics (slim/deployment/model_deploy.py:220-223,414-444): the mean of per-replica mean-loss gradients is
+    the full-batch gradient for every part of the graph without batch statistics (text tower + head)."""
+    p = O.init_params(0, "text", vocab=101)
+    bd = O.synthetic_batch(8, seed=3, vocab=101, with_images=False)
+    names = O.trainable_names(p)
+
+    def grads(sl):
+        q = {k: v.clone() for k, v in p.items()}
+        sub = {k: (v[sl] if torch.is_tensor(v) else v) for k, v in bd.items()}
+        _, _, g = O.train_step("text", q, O.TFAdam(names, q), 0.0, sub, None)
+        return g
+    full, a, b = grads(slice(0, 8)), grads(slice(0, 4)), grads(slice(4, 8))
+    for n in names:
+        assert torch.allclose((a[n] + b[n]) / 2, full[n], rtol=1e-4, atol=1e-7), n

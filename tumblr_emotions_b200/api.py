@@ -255,6 +255,28 @@ def train_text_model(train_dir, num_steps, _config=None):
     _train(TextModel, _config or TEXT_CONFIG, None, train_dir, num_steps, False)
 
 
+def gather_in_batch_order(local_logits: torch.Tensor, local_labels: torch.Tensor, nb_batches: int, batch_size: int, world: int):
+    """Batch i of `nb_batches` lives on rank i % world (round-robin sharding, no data-path collective); one all_gather at the
+    end restores the single-process order of correlation_matrix's vstack/hstack (im_text_rnn_model.py:368-373)."""
+    import torch.distributed as dist
+    classes = local_logits.shape[-1]
+    n_max = -(-nb_batches // world) * batch_size
+    pad_l = torch.zeros(n_max, classes, device=local_logits.device, dtype=local_logits.dtype)
+    pad_l[:local_logits.shape[0]] = local_logits
+    pad_y = torch.full((n_max,), -1, dtype=torch.int64, device=local_labels.device)
+    pad_y[:local_labels.shape[0]] = local_labels
+    gl = [torch.empty_like(pad_l) for _ in range(world)]
+    gy = [torch.empty_like(pad_y) for _ in range(world)]
+    dist.all_gather(gl, pad_l)
+    dist.all_gather(gy, pad_y)
+    keep = [g >= 0 for g in gy]
+    per_rank_l = [g[k].view(-1, batch_size, classes) for g, k in zip(gl, keep)]
+    per_rank_y = [g[k].view(-1, batch_size) for g, k in zip(gy, keep)]
+    logits = torch.cat([per_rank_l[i % world][i // world] for i in range(nb_batches)])
+    labels = torch.cat([per_rank_y[i % world][i // world] for i in range(nb_batches)])
+    return logits, labels
+
+
 def correlation_matrix(nb_batches, checkpoint_dir, _config=None, out_dir='data'):
     """Computes logits and labels of the input posts and saves them as numpy files (im_text_rnn_model.py:342-376).
     Forward only: is_training=False -> BN on moving statistics, no dropout.  Under torchrun the posts are sharded
@@ -281,18 +303,7 @@ def correlation_matrix(nb_batches, checkpoint_dir, _config=None, out_dir='data')
     posts_logits = logits_dev.reshape(-1, eng.nb_emotions)
     posts_labels = labels_dev.reshape(-1)
     if world > 1:
-        import torch.distributed as dist
-        n_max = -(-nb_batches // world) * batch_size
-        pad_l = torch.zeros(n_max, eng.nb_emotions, device=eng.device); pad_l[:posts_logits.shape[0]] = posts_logits
-        pad_y = torch.full((n_max,), -1, dtype=torch.int64, device=eng.device); pad_y[:posts_labels.shape[0]] = posts_labels
-        gl = [torch.empty_like(pad_l) for _ in range(world)]; gy = [torch.empty_like(pad_y) for _ in range(world)]
-        dist.all_gather(gl, pad_l); dist.all_gather(gy, pad_y)
-        keep = [g >= 0 for g in gy]
-        # restore batch order i = 0..nb_batches-1 (batch i lives on rank i % world)
-        per_rank_l = [g[k].view(-1, batch_size, eng.nb_emotions) for g, k in zip(gl, keep)]
-        per_rank_y = [g[k].view(-1, batch_size) for g, k in zip(gy, keep)]
-        posts_logits = torch.cat([per_rank_l[i % world][i // world] for i in range(nb_batches)])
-        posts_labels = torch.cat([per_rank_y[i % world][i // world] for i in range(nb_batches)])
+        posts_logits, posts_labels = gather_in_batch_order(posts_logits, posts_labels, nb_batches, batch_size, world)
     posts_logits, posts_labels = posts_logits.cpu().numpy(), posts_labels.cpu().numpy()
     if rank == 0 and out_dir is not None:
         os.makedirs(out_dir, exist_ok=True)
