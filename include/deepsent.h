@@ -80,6 +80,12 @@ int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t r
  * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w. */
 int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w,
                               int64_t cin, int ksize, uint16_t* o_hi, uint16_t* o_lo, int64_t ldo, void* stream);
+/* explicit im2col of a small-Cin strided conv (the 7x7/2 stem, image_model/inception_v1.py:63) for output rows
+ * [m_begin, m_begin + m_count): out[m - m_begin, (r*kw+s)*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c],
+ * K zero-padded to a multiple of 8; x is dense fp32 NHWC.  The rows then feed ds_conv_bf16x3 as a 1x1 GEMM. */
+int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
+                              int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
+                              uint16_t* o_lo, int64_t ldo, void* stream);
 /* HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld) and input-gradient operand [cin][kh'][kw'][cout]
  * (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout: the fused sibling 1x1 convs of an inception block share
  * one operand whose K axis is the concatenation of their output channels) as split planes; either pair may be NULL */

@@ -81,8 +81,13 @@ def test_conv_bf16x3_gemm(K, m, k, n):
     close(stats[:n], ref.sum(0), 1e-4, "stats sum")
     close(stats[n:], (ref * ref).sum(0), 1e-4, "stats sumsq")
     c.fill_(3.0)
-    K.gemm_bf16x3(A, Bt, K.View(c), bias=bias.to(DEV), flags=K.EPI_ACCUMULATE | K.EPI_RELU)
-    close(c, F.relu(ref + bias.double() + 3.0), 1e-4, "bf16x3 gemm bias+acc+relu")
+    K.gemm_bf16x3(A, Bt, K.View(c), bias=bias.to(DEV), flags=K.EPI_RELU)
+    close(c, F.relu(ref + bias.double()), 1e-4, "bf16x3 gemm bias+relu")
+    c.fill_(3.0)
+    K.gemm_bf16x3(A, Bt, K.View(c), bias=bias.to(DEV), flags=K.EPI_ACCUMULATE)      # in-L2 add (TMA reduce)
+    close(c, ref + bias.double() + 3.0, 1e-4, "bf16x3 gemm bias+accumulate")
+    with pytest.raises(RuntimeError):
+        K.gemm_bf16x3(A, Bt, K.View(c), flags=K.EPI_ACCUMULATE | K.EPI_RELU)
 
 
 def test_conv_bf16x3_exact_on_bf16_operands(K):

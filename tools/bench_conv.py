@@ -20,6 +20,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--reps", type=int, default=12)
 ap.add_argument("--old", action="store_true", help="also time the single-pass TF32 kernel")
 ap.add_argument("--stats", type=int, default=1)
+ap.add_argument("--only", default="", help="comma-separated substrings of the shape names to run")
 args = ap.parse_args()
 K.init(0)
 DEV = "cuda:0"
@@ -35,6 +36,9 @@ for name, hw in (("Mixed_3b", 28), ("Mixed_3c", 28), ("Mixed_4b", 14), ("Mixed_4
     cin = c0 + c1b + c2b + c3
 shapes += [("lstm step", 1, 1024, 4096, 1)]
 
+if args.only:
+    keys = args.only.split(",")
+    shapes = [sh for sh in shapes if any(k in sh[0] for k in keys)]
 NBUF = 3
 
 

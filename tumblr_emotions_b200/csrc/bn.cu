@@ -10,16 +10,17 @@ constexpr int RED_ROWS = 256;   // rows reduced per CTA in the column-reduction 
 
 // each thread owns one float4 column group (cg) and strides over rows; blockDim = (cgs_per_block, row_lanes)
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
-                                                       double* __restrict__ stats) {
+                                                       double* __restrict__ stats, int rows_per_cta) {
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t cg = (int64_t)blockIdx.x * cgs + threadIdx.x;
   const int64_t col = cg * 4;
-  const int64_t r0 = (int64_t)blockIdx.y * RED_ROWS;
-  const int64_t r1 = min(M, r0 + RED_ROWS);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (col < N) {
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += rl) {
-      const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + col);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
     }
@@ -101,19 +102,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t lddy,
                                                             const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const float* __restrict__ beta, double* __restrict__ sums, int64_t sums_ld) {
+                                                            const float* __restrict__ beta, double* __restrict__ sums, int64_t sums_ld,
+                                                            int rows_per_cta) {
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
-  const int64_t r0 = (int64_t)blockIdx.y * RED_ROWS;
-  const int64_t r1 = min(M, r0 + RED_ROWS);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (col < N) {
     float mu[4], rs[4], be[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { mu[j] = mean[col + j]; rs[j] = rstd[col + j]; be[j] = beta[col + j]; }
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += rl) {
-      const float4 zv = *reinterpret_cast<const float4*>(z + r * ldz + col);
-      const float4 gv = *reinterpret_cast<const float4*>(dy + r * lddy + col);
+      const float4 zv = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
       const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
       const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
@@ -182,6 +185,15 @@ dim3 red_block(int64_t N) {
   return dim3(p, 256 / p);
 }
 
+// rows reduced by one CTA: enough CTAs to fill the machine (~8 per SM), but not so many that the per-channel fp64 atomics
+// (one per CTA per channel, serialised per address in L2) dominate
+int red_rows(int64_t M, unsigned grid_x) {
+  const int64_t want_ctas = std::max<int64_t>(1, (148 * 24) / std::max(1u, grid_x));
+  int64_t rows = ds::cdiv(M, want_ctas);
+  rows = std::max<int64_t>(RED_ROWS, ds::cdiv(rows, 64) * 64);
+  return (int)rows;
+}
+
 int elementwise_blocks(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(ds::cdiv(total, 256), 148 * 16)); }
 
 }  // namespace
@@ -192,8 +204,10 @@ int ds_colstats(const float* z, int64_t ldz, int64_t m, int64_t n, double* stats
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
   const dim3 blk = red_block(n);
-  dim3 grid((unsigned)ds::cdiv(n / 4, blk.x), (unsigned)ds::cdiv(m, RED_ROWS));
-  colstats_kernel<<<grid, blk, 0, ds::S(stream)>>>(z, ldz, m, n, stats);
+  const unsigned gx = (unsigned)ds::cdiv(n / 4, blk.x);
+  const int rows = red_rows(m, gx);
+  dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
+  colstats_kernel<<<grid, blk, 0, ds::S(stream)>>>(z, ldz, m, n, stats, rows);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -224,8 +238,10 @@ int ds_bn_relu_bwd_reduce(const float* dy, int64_t lddy, const float* z, int64_t
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
   const dim3 blk = red_block(n);
-  dim3 grid((unsigned)ds::cdiv(n / 4, blk.x), (unsigned)ds::cdiv(m, RED_ROWS));
-  bn_bwd_reduce_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld);
+  const unsigned gx = (unsigned)ds::cdiv(n / 4, blk.x);
+  const int rows = red_rows(m, gx);
+  dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
+  bn_bwd_reduce_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, rows);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -12,9 +12,13 @@
 //                     unit walks the 128 pixels across rows / images and zero-fills the halo), B_hi, B_lo.
 //   warp 1 / lane 0 : MMA issuer.  3 x tcgen05.mma (M=128, N=BN, K=16) per 16 channels into one of two TMEM
 //                     accumulators (2 x 256 columns); tcgen05.commit releases ring slots and publishes the accumulator.
-//   warps 2-5       : epilogue, overlapped with the next tile's main loop.  TMEM -> registers (tcgen05.ld 32x32b.x32),
-//                     scale / bias / ReLU / accumulate, optional per-channel sum and sum-of-squares for batch-norm
-//                     (butterfly reduce + fp64 atomics), fp32 stores (plain or atomic for split-K).
+//   warps 2-5       : epilogue, overlapped with the next tile's main loop.  Per 32 output columns: TMEM -> registers
+//                     (tcgen05.ld 32x32b.x32), scale / bias / ReLU, swizzled st.shared into a 128x32 fp32 staging tile, then
+//                     ONE TMA store (cp.async.bulk.tensor) - or TMA reduce-add for the accumulate / split-K epilogues -
+//                     writes it coalesced and clips the M / N edges.  Batch-norm statistics: each thread sums one staged
+//                     column over its warp's 32 rows into fp64 registers that live for the whole kernel (the grid is a
+//                     multiple of the column-tile count, so a CTA keeps the same output columns for all its tiles) and
+//                     are flushed with one global atomic per channel per CTA.
 // Replaces the slim.conv2d sites of image_model/inception_v1.py:71-247, their input gradients (same contraction on
 // flipped weights), the weight gradients of Mixed_5c (:229-248, as pixel-major GEMMs with split-K) and the LSTM
 // products of image_text_model/im_text_rnn_model.py:89-90.
@@ -32,6 +36,7 @@ constexpr int A_TILE_BYTES = BM * 128;     // 16 KB per plane
 constexpr int MAX_STAGES = 8;
 constexpr int ACC_COLS = 256;              // TMEM columns per accumulator buffer
 constexpr int THREADS = 192;
+constexpr int STG_BYTES = BM * 32 * 4;     // one epilogue staging tile: 128 rows x 32 fp32 columns
 
 struct Params {
   int64_t M, N, ldc;
@@ -51,7 +56,7 @@ struct Params {
   int ipz;           // K iterations per split
   int h, w, pad;
   int stages;
-  int smem_stats;    // 1: batch-norm partial sums accumulate in shared memory (N <= 1024), 0: straight to global atomics
+  int nstg;          // epilogue staging tiles (1 or 2)
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t& m0, int& n0, int& it0, int& it1) {
@@ -65,27 +70,29 @@ __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t&
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
-  const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;   // 1024-aligned
+  const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;   // epilogue staging tiles (1024-aligned, 16 KB each)
+  const uint32_t bars = stg0 + (uint32_t)p.nstg * STG_BYTES;
   // full[s] at bars + 8*s, empty[s] at bars + 64 + 8*s, tmem_full[b] at bars + 128 + 8*b, tmem_empty[b] at bars + 144 + 8*b,
   // tmem base pointer at bars + 160
   const uint32_t full0 = bars, empty0 = bars + 64, tfull0 = bars + 128, tempty0 = bars + 144, tmem_slot = bars + 160;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
-  // per-CTA batch-norm partial sums [2][N] (fp64), flushed with one global atomic per column when the CTA retires
-  double* sstats = reinterpret_cast<double*>(smem_raw + (bars + 256 - raw));
+  // cross-warp reduction of the batch-norm partial sums of this CTA's column tile: [2][bn] fp64
+  double* sred = reinterpret_cast<double*>(smem_raw + (bars + 256 - raw));
   const bool do_stats = (p.flags & DS_EPI_STATS) != 0;
-  if (do_stats && p.smem_stats)
-    for (int i = threadIdx.x; i < 2 * (int)p.N; i += THREADS) sstats[i] = 0.0;
+  if (do_stats)
+    for (int i = threadIdx.x; i < 2 * p.bn; i += THREADS) sred[i] = 0.0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmC);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -178,115 +185,111 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   } else {
     // ---------------- epilogue (warps 2..5; warp w owns TMEM lanes 32*(w%4) .. +31) ----------------
     const int quarter = warp & 3;
-    const bool atomic = p.ksplit > 1;
-    uint32_t acc_it = 0;
+    const int r = quarter * 32 + lane;                 // row of the tile owned by this thread
+    const bool leader = threadIdx.x == 64;             // issues the TMA stores and tracks their bulk groups
+    const bool reduce_add = p.ksplit > 1 || (p.flags & DS_EPI_ACCUMULATE);
+    double s1acc[ACC_COLS / 32], s2acc[ACC_COLS / 32];
+#pragma unroll
+    for (int i = 0; i < ACC_COLS / 32; ++i) { s1acc[i] = 0.0; s2acc[i] = 0.0; }
+    uint32_t acc_it = 0, chunk_it = 0;
+    int n0_cta = 0;
     for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
       int64_t m0; int n0, it0, it1;
       tile_coords(p, t, m0, n0, it0, it1);
+      n0_cta = n0;
       const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
       mbar_wait(tfull0 + 8 * buf, aph);
       tc_fence_after();
-      const int64_t row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* crow = p.c + row * p.ldc;
       const uint32_t tbase = tmem_base + buf * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       const bool first_split = it0 == 0;
-      const int col_end = (int)min((int64_t)(n0 + p.bn), p.N);     // columns owned by this tile
-      for (int cb = 0; cb < p.bn; cb += 32) {
+#pragma unroll
+      for (int ci = 0; ci < ACC_COLS / 32; ++ci) {
+        const int cb = ci * 32;
         const int col0 = n0 + cb;
-        if (col0 >= col_end) break;                  // warp-uniform
+        if (cb >= p.bn || col0 >= p.N) break;          // CTA-uniform
+        const uint32_t stg = stg0 + (p.nstg == 2 ? (chunk_it & 1u) * STG_BYTES : 0u);
+        // the TMA store that last read this staging tile must have finished reading it
+        if (leader) { if (p.nstg == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
         float v[32];
         tmem_ld32(tbase + (uint32_t)cb, v);
-        if (do_stats) {
-          // per-column sum and sum of squares over this warp's 32 rows: butterfly transpose-reduce, column j -> lane j
-          float s1[32], s2[32];
+        if (p.scale || (p.bias && first_split) || (p.flags & DS_EPI_RELU)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = row_ok ? v[j] : 0.f;
-            s1[j] = x;
-            s2[j] = x * x;
-          }
-#pragma unroll
-          for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
-            const bool hi = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float send1 = hi ? s1[i] : s1[i + half];
-              const float keep1 = hi ? s1[i + half] : s1[i];
-              const float send2 = hi ? s2[i] : s2[i + half];
-              const float keep2 = hi ? s2[i + half] : s2[i];
-              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-            }
-          }
-          // after the 5 rounds lane l holds column bitrev-free index: round with offset `off` keeps the upper half on
-          // lanes with that bit set, so lane l owns column l
-          const int col = col0 + lane;
-          if (col < col_end) {
-            double* dst = p.smem_stats ? sstats : p.stats;
-            atomicAdd(dst + col, (double)s1[0]);
-            atomicAdd(dst + p.N + col, (double)s2[0]);
+            const int col = min(col0 + j, (int)p.N - 1);
+            float x = v[j];
+            if (p.scale) x *= __ldg(p.scale + col);
+            if (p.bias && first_split) x += __ldg(p.bias + col);
+            if (p.flags & DS_EPI_RELU) x = fmaxf(x, 0.f);
+            v[j] = x;
           }
         }
-        if (row_ok) {
+        named_bar_sync(1, 128);                        // staging tile free (leader's wait above) ...
+        const uint32_t srow = stg + (uint32_t)r * 128u;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int col = col0 + j;
-            if (col < col_end) {                     // N, bn % 4 == 0 -> whole float4 valid
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.scale) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-                o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
-              }
-              if (p.bias && first_split) {
-                const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
-              }
-              float4* dst = reinterpret_cast<float4*>(crow + col);
-              if (atomic) {
-                atomicAdd(crow + col, o.x); atomicAdd(crow + col + 1, o.y);
-                atomicAdd(crow + col + 2, o.z); atomicAdd(crow + col + 3, o.w);
-              } else {
-                if (p.flags & DS_EPI_ACCUMULATE) {
-                  const float4 q = *dst;
-                  o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                }
-                if (p.flags & DS_EPI_RELU) {
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                }
-                *dst = o;
-              }
-            }
-          }
+        for (int j = 0; j < 8; ++j)                    // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+          st_shared_v4(srow + (uint32_t)((j ^ (r & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        named_bar_sync(1, 128);                        // ... and now completely written
+        if (leader) {
+          if (reduce_add) tma_reduce_add_2d(&tmC, stg, col0, (int32_t)m0);
+          else tma_store_2d(&tmC, stg, col0, (int32_t)m0);
+          bulk_commit();
         }
+        if (do_stats) {
+          // column `lane` of the staged tile over this warp's 32 rows (bank-conflict free: a row's 128 bytes span all banks)
+          float a1 = 0.f, a2 = 0.f;
+          const uint32_t cchunk = (uint32_t)lane >> 2, cin4 = ((uint32_t)lane & 3u) << 2;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t row = (uint32_t)(quarter * 32 + rr);
+            const float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
+            a1 += x;
+            a2 = fmaf(x, x, a2);
+          }
+          s1acc[ci] += (double)a1;
+          s2acc[ci] += (double)a2;
+        }
+        ++chunk_it;
       }
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    if (do_stats && p.smem_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
-      for (int i = threadIdx.x - 64; i < 2 * (int)p.N; i += 128) {
-        const double v = sstats[i];
-        if (v != 0.0) atomicAdd(p.stats + i, v);
+    if (do_stats) {
+      // 4 warps x 32 rows -> one value per column (shared fp64 atomics, once per CTA), then one global atomic per column
+#pragma unroll
+      for (int ci = 0; ci < ACC_COLS / 32; ++ci) {
+        if (ci * 32 < p.bn) {
+          atomicAdd(sred + ci * 32 + lane, s1acc[ci]);
+          atomicAdd(sred + p.bn + ci * 32 + lane, s2acc[ci]);
+        }
+      }
+      named_bar_sync(1, 128);
+      for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
+        const int col = n0_cta + i;
+        if (col < p.N) {
+          atomicAdd(p.stats + col, sred[i]);
+          atomicAdd(p.stats + p.N + col, sred[p.bn + i]);
+        }
       }
     }
+    if (leader) bulk_wait<0>();                        // every store has landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
-int pick_bn(int64_t m, int64_t n, int sms) {
-  // fewest column tiles (each a multiple of 16, <= 256, as even as possible); when that leaves SMs idle (small-M
+int pick_bn(int64_t m, int64_t n, int ksplit, int sms) {
+  // fewest column tiles (each a multiple of 32, <= 256, as even as possible); when that leaves SMs idle (small-M
   // products such as the LSTM step) split N further, down to 32-wide tiles
-  const int64_t tiles_m = (m + BM - 1) / BM;
+  const int64_t tiles_m = ((m + BM - 1) / BM) * ksplit;
   int64_t tiles_n = (n + 255) / 256;
   while (tiles_m * tiles_n < sms && (n + tiles_n) / (tiles_n + 1) >= 32) ++tiles_n;
   int bn = (int)((n + tiles_n - 1) / tiles_n);
-  bn = (bn + 15) / 16 * 16;
-  return bn < 16 ? 16 : bn;
+  bn = (bn + 31) / 32 * 32;           // the epilogue stores 32-column boxes: a tile owns whole boxes
+  return bn < 32 ? 32 : bn;
 }
 
 }  // namespace
@@ -305,20 +308,22 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   Params p;
   p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags;
-  p.bn = ds::g_debug[1] > 0 ? ds::g_debug[1] : pick_bn(M, n, sms);
-  p.tiles_n = (int)ds::cdiv(n, p.bn);
   p.ksize = ksize; p.cin = (int)cin; p.cpt = (int)((cin + KC - 1) / KC);
   p.iters = ksize * ksize * p.cpt;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > p.iters) ksplit = p.iters;
   p.ipz = (int)ds::cdiv(p.iters, ksplit);
   p.ksplit = (int)ds::cdiv(p.iters, p.ipz);
+  p.bn = ds::g_debug[1] > 0 ? ds::g_debug[1] : pick_bn(M, n, p.ksplit, sms);
+  p.tiles_n = (int)ds::cdiv(n, p.bn);
   DS_REQUIRE(p.ksplit == 1 || !(flags & (DS_EPI_RELU | DS_EPI_STATS)), "split-K adds atomically: no ReLU / stats epilogue");
+  DS_REQUIRE(!((flags & DS_EPI_ACCUMULATE) && (flags & (DS_EPI_RELU | DS_EPI_STATS))), "the accumulate epilogue is an in-L2 add: no ReLU / stats");
+  DS_REQUIRE(p.bn % 32 == 0 && p.bn >= 32 && p.bn <= 256, "column tile must be a multiple of 32 in [32, 256]");
   p.tiles = ds::cdiv(M, BM) * p.tiles_n * p.ksplit;
   p.h = (int)h; p.w = (int)w; p.pad = (ksize - 1) / 2;
   const int64_t ktot = (int64_t)ksize * ksize * cin;
 
-  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
   int r = 0;
   for (int plane = 0; plane < 2 && !r; ++plane) {
     CUtensorMap* tm = plane ? &tmAl : &tmAh;
@@ -331,23 +336,31 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   if (!r) r = ds::make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)p.bn);
   if (r) return ds::fail("cuTensorMapEncode(B) failed: CUresult %d (n=%lld ktot=%lld ldb=%lld bn=%d)", r, (long long)n, (long long)ktot, (long long)ldb, p.bn);
 
+  r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d (M=%lld n=%lld ldc=%lld)", r, (long long)M, (long long)n, (long long)ldc);
+
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
-  p.smem_stats = ((flags & DS_EPI_STATS) && n <= 1024) ? 1 : 0;
-  const int stats_bytes = p.smem_stats ? (int)(2 * n * sizeof(double)) : 0;
-  int stages = (226 * 1024 - 1024 - 256 - stats_bytes) / stage_bytes;
+  const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);      // alignment slack, barriers, stats reduction
+  p.nstg = (226 * 1024 - fixed - 2 * STG_BYTES) / stage_bytes >= 2 ? 2 : 1;
+  int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES) / stage_bytes;
   if (ds::g_debug[2] > 0) stages = ds::g_debug[2];
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + stats_bytes;
+  size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + fixed;
+  DS_REQUIRE(smem <= 227 * 1024, "shared-memory budget exceeded");
   if (smem < 120 * 1024) smem = 120 * 1024;     // one CTA per SM: each CTA owns all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
     DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, sms);
-  conv_bf16x3_kernel<<<grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, p);
+  // a CTA must keep the same column tile for all its tiles (register-resident batch-norm partial sums): with tiles
+  // ordered column-tile fastest that holds when the grid is a multiple of the column-tile count
+  int64_t grid = std::min<int64_t>(p.tiles, sms);
+  if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
+  DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
+  conv_bf16x3_kernel<<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -39,34 +39,51 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
   }
 }
 
-// gather formulation: every input pixel sums the dy of the windows whose recorded argmax is this pixel (deterministic)
+// gather formulation: every input pixel sums the dy of the windows whose recorded argmax is this pixel (deterministic).
+// The (at most NW x NW) candidate windows are fully unrolled: all argmax words are fetched first, dy is only fetched for the
+// windows that actually selected this pixel in one of the thread's 4 channels.
+template <int K, int S>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, int64_t lddy,
                                                           const uint8_t* __restrict__ argmax, int64_t B, int h, int w, int c4,
-                                                          int k, int stride, int pad_t, int pad_l, int ho, int wo,
+                                                          int pad_t, int pad_l, int ho, int wo,
                                                           float* __restrict__ dx, int64_t lddx, int accumulate) {
-  const int64_t total = B * h * w * (int64_t)c4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    int64_t t = i / c4;
-    const int iw = (int)(t % w); t /= w;
-    const int ih = (int)(t % h);
-    const int64_t b = t / h;
-    float acc[4] = {0, 0, 0, 0};
-    // windows p with p*stride - pad_t <= ih <= p*stride - pad_t + k - 1
-    const int p_lo = max(0, (ih + pad_t - k + 1 + stride - 1) / stride), p_hi = min(ho - 1, (ih + pad_t) / stride);
-    const int q_lo = max(0, (iw + pad_l - k + 1 + stride - 1) / stride), q_hi = min(wo - 1, (iw + pad_l) / stride);
-    for (int p = p_lo; p <= p_hi; ++p) {
-      const int r = ih - (p * stride - pad_t);
-      for (int q = q_lo; q <= q_hi; ++q) {
-        const int s = iw - (q * stride - pad_l);
-        const int me = r * k + s;
-        const int64_t o = ((b * ho + p) * (int64_t)wo + q);
-        const uchar4 a = *reinterpret_cast<const uchar4*>(argmax + (o * c4 + cg) * 4);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o * lddy + cg * 4));
-        if (a.x == me) acc[0] += g.x;
-        if (a.y == me) acc[1] += g.y;
-        if (a.z == me) acc[2] += g.z;
-        if (a.w == me) acc[3] += g.w;
+  constexpr int NW = (K + S - 1) / S;
+  // one CTA per input row (b, ih): a single 32-bit division per work item instead of a div/mod chain
+  const int64_t b = blockIdx.x / (uint32_t)h;
+  const int ih = (int)(blockIdx.x - b * h);
+  const uint32_t row_items = (uint32_t)w * (uint32_t)c4;
+  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
+    const int iw = (int)(i / (uint32_t)c4);
+    const int cg = (int)(i - (uint32_t)iw * (uint32_t)c4);
+    const int p_hi = (ih + pad_t) / S, q_hi = (iw + pad_l) / S;
+    uint32_t am[NW * NW];
+    uint32_t me[NW * NW];
+    int64_t oo[NW * NW];
+#pragma unroll
+    for (int a = 0; a < NW; ++a)
+#pragma unroll
+      for (int c = 0; c < NW; ++c) {
+        const int p = p_hi - a, q = q_hi - c;
+        const int r = ih + pad_t - p * S, s = iw + pad_l - q * S;
+        const bool v = p >= 0 && p < ho && q >= 0 && q < wo && r < K && s < K;
+        const int64_t o = ((b * ho + (v ? p : 0)) * (int64_t)wo + (v ? q : 0));
+        oo[a * NW + c] = o;
+        me[a * NW + c] = v ? (uint32_t)(r * K + s) : 0xffu;      // 0xff never matches a recorded in-window argmax of a valid tap
+        am[a * NW + c] = __ldg(reinterpret_cast<const uint32_t*>(argmax + (o * c4 + cg) * 4));
+      }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < NW * NW; ++n) {
+      const uint32_t m = me[n];
+      if (m == 0xffu) continue;
+      const uint32_t a4 = am[n];
+      const bool m0 = (a4 & 0xffu) == m, m1 = ((a4 >> 8) & 0xffu) == m, m2 = ((a4 >> 16) & 0xffu) == m, m3 = (a4 >> 24) == m;
+      if (m0 | m1 | m2 | m3) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + oo[n] * lddy + cg * 4));
+        if (m0) acc[0] += g.x;
+        if (m1) acc[1] += g.y;
+        if (m2) acc[2] += g.z;
+        if (m3) acc[3] += g.w;
       }
     }
     float4* dst = reinterpret_cast<float4*>(dx + ((b * h + ih) * (int64_t)w + iw) * lddx + cg * 4);
@@ -157,9 +174,20 @@ int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t
                    void* stream) {
   DS_REQUIRE(c % 4 == 0 && lddx % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
   const int64_t total = batch * h * w * (c / 4);
+  DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
-  maxpool_bwd_kernel<<<blocks_for(total), 256, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), k, stride,
-                                                                pad_t, pad_l, (int)ho, (int)wo, dx, lddx, accumulate);
+  const int blocks = (int)(batch * h);
+  DS_REQUIRE(batch * h < (int64_t)1 << 31, "too many rows");
+#define DS_POOL_BWD(KK, SS)                                                                                                   \
+  maxpool_bwd_kernel<KK, SS><<<blocks, 256, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), pad_t, pad_l, \
+                                                               (int)ho, (int)wo, dx, lddx, accumulate)
+  if (k == 3 && stride == 1) DS_POOL_BWD(3, 1);
+  else if (k == 3 && stride == 2) DS_POOL_BWD(3, 2);
+  else if (k == 2 && stride == 2) DS_POOL_BWD(2, 2);
+  else if (k == 2 && stride == 1) DS_POOL_BWD(2, 1);
+  else if (k == 3 && stride == 3) DS_POOL_BWD(3, 3);
+  else return ds::fail("ds_maxpool_bwd: unsupported window %dx%d stride %d", k, k, stride);
+#undef DS_POOL_BWD
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@
 namespace {
 
 int ew_blocks(int64_t total, int per_block = 256) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ds::cdiv(total, per_block), 148 * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ds::cdiv(total, per_block), 148 * (2048 / per_block)));
 }
 
 // ---- fp32 <-> split ------------------------------------------------------------------------------------------------
@@ -106,48 +106,59 @@ __global__ void bn_dbeta_kernel(const double* __restrict__ sums, int n, float* _
 }
 
 // ---- pooling on split activations ----------------------------------------------------------------------------------
+// 8 channels per thread (16-byte loads per plane); the K x K window is fully unrolled with clamped coordinates and validity
+// predicates so that all 2*K*K loads are in flight together.  First maximum in scan order wins (TF MaxPool / MaxPoolGrad).
+template <int K>
 __global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
-                                                                int64_t ldx, int64_t B, int h, int w, int c4, int k, int stride,
+                                                                int64_t ldx, int64_t B, int h, int w, int c8, int stride,
                                                                 int pad_t, int pad_l, int ho, int wo, uint16_t* __restrict__ y_hi,
                                                                 uint16_t* __restrict__ y_lo, int64_t ldy,
                                                                 uint8_t* __restrict__ argmax) {
-  const uint32_t total = (uint32_t)(B * ho * wo * (int64_t)c4);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cg = (int)(i % (uint32_t)c4);
-    uint32_t t = i / (uint32_t)c4;
-    const int q = (int)(t % (uint32_t)wo); t /= (uint32_t)wo;
-    const int p = (int)(t % (uint32_t)ho);
-    const int64_t b = t / (uint32_t)ho;
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    uint2 bh = make_uint2(0, 0), bl = make_uint2(0, 0);
-    uint32_t bhv[4] = {0, 0, 0, 0}, blv[4] = {0, 0, 0, 0};
-    int arg[4] = {255, 255, 255, 255};
-    for (int r = 0; r < k; ++r) {
-      const int ih = p * stride - pad_t + r;
-      if (ih < 0 || ih >= h) continue;
-      for (int s = 0; s < k; ++s) {
-        const int iw = q * stride - pad_l + s;
-        if (iw < 0 || iw >= w) continue;
-        const int64_t off = ((b * h + ih) * (int64_t)w + iw) * ldx + cg * 4;
-        const uint2 hv = __ldg(reinterpret_cast<const uint2*>(x_hi + off));
-        const uint2 lv = __ldg(reinterpret_cast<const uint2*>(x_lo + off));
-        const uint32_t hh[4] = {hv.x & 0xffffu, hv.x >> 16, hv.y & 0xffffu, hv.y >> 16};
-        const uint32_t ll[4] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16};
+  // one CTA per output row (b, p): a single 32-bit division per work item instead of a div/mod chain
+  const int64_t b = blockIdx.x / (uint32_t)ho;
+  const int p = (int)(blockIdx.x - b * ho);
+  const uint32_t row_items = (uint32_t)wo * (uint32_t)c8;
+  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
+    const int q = (int)(i / (uint32_t)c8);
+    const int cg = (int)(i - (uint32_t)q * (uint32_t)c8);
+    const int ih0 = p * stride - pad_t, iw0 = q * stride - pad_l;
+    uint4 hv[K * K], lv[K * K];
+    bool ok[K * K];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v = ds::merge_bf16(hh[j], ll[j]);
-          if (v > best[j] || arg[j] == 255) { best[j] = v; arg[j] = r * k + s; bhv[j] = hh[j]; blv[j] = ll[j]; }
-        }
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const int ih = ih0 + r, iw = iw0 + s;
+        const bool v = ih >= 0 && ih < h && iw >= 0 && iw < w;
+        ok[r * K + s] = v;
+        const int64_t off = ((b * h + (v ? ih : 0)) * (int64_t)w + (v ? iw : 0)) * ldx + cg * 8;
+        hv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
+        lv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+      }
+    float best[8];
+    uint32_t bh[8], bl[8], arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0; bl[j] = 0; arg[j] = 255; }
+#pragma unroll
+    for (int tp = 0; tp < K * K; ++tp) {
+      if (!ok[tp]) continue;
+      const uint32_t hw[4] = {hv[tp].x, hv[tp].y, hv[tp].z, hv[tp].w}, lw[4] = {lv[tp].x, lv[tp].y, lv[tp].z, lv[tp].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t hh = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu);
+        const uint32_t ll = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
+        const float v = ds::merge_bf16(hh, ll);
+        if (v > best[j] || arg[j] == 255) { best[j] = v; arg[j] = tp; bh[j] = hh; bl[j] = ll; }
       }
     }
-    bh = make_uint2(bhv[0] | (bhv[1] << 16), bhv[2] | (bhv[3] << 16));
-    bl = make_uint2(blv[0] | (blv[1] << 16), blv[2] | (blv[3] << 16));
     const int64_t o = ((b * ho + p) * (int64_t)wo + q);
-    *reinterpret_cast<uint2*>(y_hi + o * ldy + cg * 4) = bh;
-    *reinterpret_cast<uint2*>(y_lo + o * ldy + cg * 4) = bl;
+    *reinterpret_cast<uint4*>(y_hi + o * ldy + cg * 8) =
+        make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
+    *reinterpret_cast<uint4*>(y_lo + o * ldy + cg * 8) =
+        make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
     if (argmax) {
-      uchar4 a = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
-      *reinterpret_cast<uchar4*>(argmax + (o * c4 + cg) * 4) = a;
+      *reinterpret_cast<uint2*>(argmax + (o * c8 + cg) * 8) =
+          make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24), arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24));
     }
   }
 }
@@ -213,6 +224,48 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
       const int64_t off = ((int64_t)tap * cin + c) * ldo + m;
       o_hi[off] = th[threadIdx.x][i]; o_lo[off] = tl[threadIdx.x][i];
     }
+  }
+}
+
+// Explicit im2col of a small-Cin strided convolution (the 7x7/2 stem, image_model/inception_v1.py:63) into the split-bf16
+// GEMM operand: out[m, (r*kw + s)*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c] (0 outside), K padded
+// with zeros to k8 = roundup(kh*kw*cin, 8).  One thread per (output pixel, 8 consecutive K entries): 16-byte stores.
+template <int CIN_T, int KW_T>   // 0 = runtime value
+__global__ void __launch_bounds__(256) im2col_small_cin_kernel(const float* __restrict__ x, int64_t m_begin, int64_t m_count, int h, int w,
+                                                               int cin_rt, int kh, int kw_rt, int stride, int pad_t, int pad_l, int ho,
+                                                               int wo, uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
+                                                               int64_t ldo, int k8) {
+  const int cin = CIN_T ? CIN_T : cin_rt, kw = KW_T ? KW_T : kw_rt;
+  const int groups = k8 >> 3;
+  const int K = kh * kw * cin;
+  const int64_t total = m_count * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t ml = i / groups;
+    const int64_t m = m_begin + ml;
+    const int q = (int)(m % wo);
+    const int64_t t2 = m / wo;
+    const int p = (int)(t2 % ho);
+    const int64_t b = t2 / ho;
+    const int ih0 = p * stride - pad_t, iw0 = q * stride - pad_l;
+    const float* xb = x + b * (int64_t)h * w * cin;
+    uint32_t hh[8], ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int c = k % cin;
+        const int t = k / cin;
+        const int s = t % kw, r = t / kw;
+        const int ih = ih0 + r, iw = iw0 + s;
+        if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(xb + ((int64_t)ih * w + iw) * cin + c);
+      }
+      ds::split_bf16(v, hh[j], ll[j]);
+    }
+    const int64_t o = ml * ldo + g * 8;
+    *reinterpret_cast<uint4*>(o_hi + o) = make_uint4(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16), hh[4] | (hh[5] << 16), hh[6] | (hh[7] << 16));
+    *reinterpret_cast<uint4*>(o_lo + o) = make_uint4(ll[0] | (ll[1] << 16), ll[2] | (ll[3] << 16), ll[4] | (ll[5] << 16), ll[6] | (ll[7] << 16));
   }
 }
 
@@ -298,13 +351,18 @@ int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream) {
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,
                          int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo, uint16_t* y_hi, uint16_t* y_lo,
                          int64_t ldy, uint8_t* argmax, void* stream) {
-  DS_REQUIRE(c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
-  DS_REQUIRE(k * k < 255, "window too large for uint8 argmax");
-  const int64_t total = batch * ho * wo * (c / 4);
+  DS_REQUIRE(c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "channel counts must be multiples of 8");
+  DS_REQUIRE((((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0, "16-byte aligned planes");
+  DS_REQUIRE(k == 2 || k == 3, "2x2 and 3x3 windows");
+  const int64_t total = batch * ho * wo * (c / 8);
   DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
-  maxpool_fwd_split_kernel<<<ew_blocks(total), 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 4), k, stride,
-                                                                      pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
+  if (k == 3)
+    maxpool_fwd_split_kernel<3><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
+                                                                                pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
+  else
+    maxpool_fwd_split_kernel<2><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
+                                                                                pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -328,6 +386,26 @@ int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_
   dim3 grid((unsigned)ds::cdiv(M, 32), (unsigned)ds::cdiv(cin, 32), (unsigned)(ksize * ksize));
   im2col_transpose_split_kernel<<<grid, dim3(32, 8), 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize,
                                                                        (ksize - 1) / 2, o_hi, o_lo, ldo);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
+                              int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
+                              uint16_t* o_lo, int64_t ldo, void* stream) {
+  const int k8 = (int)((kh * kw * cin + 7) / 8 * 8);
+  DS_REQUIRE(ldo % 8 == 0 && ldo >= k8, "output row stride must be a multiple of 8 and cover the padded K");
+  DS_REQUIRE((((uintptr_t)o_hi | (uintptr_t)o_lo) & 15) == 0, "16-byte aligned planes");
+  DS_REQUIRE(m_begin >= 0 && m_begin + m_count <= batch * ho * wo, "row range outside the output");
+  if (m_count == 0) return 0;
+  if (cin == 3 && kw == 7)
+    im2col_small_cin_kernel<3, 7><<<ew_blocks(m_count * (k8 / 8)), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, (int)cin, kh,
+                                                                                          kw, stride, pad_t, pad_l, (int)ho, (int)wo, o_hi,
+                                                                                          o_lo, ldo, k8);
+  else
+    im2col_small_cin_kernel<0, 0><<<ew_blocks(m_count * (k8 / 8)), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, (int)cin, kh,
+                                                                                          kw, stride, pad_t, pad_l, (int)ho, (int)wo, o_hi,
+                                                                                          o_lo, ldo, k8);
   DS_LAUNCH_CHECK();
   return 0;
 }

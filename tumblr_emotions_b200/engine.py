@@ -70,9 +70,17 @@ class ConvUnit:
             c += n
         self.trainable = scopes[0].startswith(TRAINABLE_WEIGHT_PREFIXES)
         kk = k * k
+        # the 7x7/2 stem (cin = 3): explicit im2col into an L2-sized split-bf16 scratch, then the same tensor-core GEMM
+        self.stem_tc = self.split and not self.tc and dx is None
         if self.tc:
             self.w_fwd = SView(eng.new_split((self.N,), kk * cin))           # [N][r][s][cin]
             self.w_dgrad = SView(eng.new_split((cin,), kk * self.N))         # [cin][r'][s'][N]
+        elif self.stem_tc:
+            self.k8 = (kk * cin + 7) // 8 * 8
+            self.w_fwd = SView(eng.new_split((self.N,), self.k8))            # [N][(r,s,c) zero-padded to k8]
+            self.w_dgrad = None
+            self.chunk_imgs = min(eng.batch, 16)                             # 16 images x 12544 pixels x 608 B = 122 MB ~ L2
+            self.col = SView(eng.new_split((self.chunk_imgs * self.h_out * self.h_out,), self.k8))
         else:
             self.w_fwd = None
             self.w_dgrad = eng.new(cin, kk * self.N)                          # fp32 [cin][r'][s'][N]
@@ -91,6 +99,8 @@ class ConvUnit:
             w = e.weight(s + "/weights")
             if self.tc:
                 ops.repack_conv_weights_split(w, fwd=self.w_fwd.rows_slice(c, n), dgrad=self.w_dgrad.slice(c, n), dgrad_tap=self.N)
+            elif self.stem_tc:
+                ops.repack_conv_weights_split(w, fwd=self.w_fwd)
             else:
                 ops.repack_conv_weights(w, fwd=None, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
                                         round_tf32=False)
@@ -115,6 +125,14 @@ class ConvUnit:
         Zv = View(self.Z)
         if self.tc:
             ops.conv_bf16x3(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.N, Zv, stats=self.stats if train else None)
+        elif self.stem_tc:
+            px = self.h_out * self.h_out
+            for b0 in range(0, B, self.chunk_imgs):
+                nb = min(self.chunk_imgs, B - b0)
+                ops.im2col_small_cin_split(self.x.base, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out,
+                                           self.h_out, b0 * px, nb * px, self.col)
+                ops.conv_bf16x3(self.col.rows_slice(0, nb * px), nb * px, 1, 1, self.k8, 1, self.w_fwd, self.N,
+                                View(self.Z[b0 * px:(b0 + nb) * px]), stats=self.stats if train else None)
         else:
             if len(self.scopes) == 1:
                 ops.conv_simt(self.x, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
@@ -577,8 +595,9 @@ class Engine:
             ops.lstm_gates_bwd(self.G[t], self.C[t], self.C[t + 1], self.seq_lens, t, B, n, self.dh_rec if t < T - 1 else None,
                                self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], dzs)
             if t > 0:
-                if self.split:
-                    ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec))
+                if self.split:      # K = 4n is long and M x N small: split-K keeps all SMs busy with 8x less operand traffic
+                    self.dh_rec.zero_()
+                    ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec), ksplit=8)
                 else:
                     ops.gemm_nt(View(self.DZ[t * B:(t + 1) * B]), View(kern[e:]), View(self.dh_rec))
         dk = self.grad("Text/rnn/basic_lstm_cell/kernel")

@@ -127,6 +127,11 @@ def im2col_transpose_split(x: SView, batch, h, w, cin, ksize, out: SView):
     lib().im2col_transpose_split(x.ptr, x.lo_ptr, x.ld, batch, h, w, cin, ksize, out.ptr, out.lo_ptr, out.ld, _stream())
 
 
+def im2col_small_cin_split(x: torch.Tensor, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, m_begin, m_count, out: SView):
+    lib().im2col_small_cin_split(x.data_ptr(), batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, m_begin, m_count, out.ptr,
+                                 out.lo_ptr, out.ld, _stream())
+
+
 def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None):
     """dgrad: SView over the [cin, kh*kw*dgrad_tap] operand, already sliced to this conv's channel offset"""
     kh, kw, cin, cout = hwio.shape
