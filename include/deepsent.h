@@ -80,24 +80,32 @@ int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t r
  * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w. */
 int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w,
                               int64_t cin, int ksize, uint16_t* o_hi, uint16_t* o_lo, int64_t ldo, void* stream);
-/* explicit im2col of a small-Cin strided conv (the 7x7/2 stem, image_model/inception_v1.py:63) for output rows
- * [m_begin, m_begin + m_count): out[m - m_begin, (r*kw+s)*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c],
- * K zero-padded to a multiple of 8; x is dense fp32 NHWC.  The rows then feed ds_conv_bf16x3 as a 1x1 GEMM. */
+/* explicit im2col of the 7x7/2 stem conv (image_model/inception_v1.py:63; cin = 3, kw = 7) for output rows
+ * [m_begin, m_begin + m_count): out[m - m_begin, r*kg + s*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c] with
+ * kg = roundup(kw*cin, 8) (each filter row is a zero-padded group of whole 16-byte stores); x is dense fp32 NHWC.  The rows then
+ * feed ds_conv_bf16x3 as a 1x1 GEMM with K = kh*kg against weights repacked with fwd_rs = kg. */
 int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
                               int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
                               uint16_t* o_lo, int64_t ldo, void* stream);
-/* HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld) and input-gradient operand [cin][kh'][kw'][cout]
- * (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout: the fused sibling 1x1 convs of an inception block share
+/* HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld; filter-row stride fwd_rs, 0 = kw*cin) and
+ * input-gradient operand [cin][kh'][kw'][cout] (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout: the fused sibling 1x1 convs of an inception block share
  * one operand whose K axis is the concatenation of their output channels) as split planes; either pair may be NULL */
 int ds_repack_conv_weights_split(const float* hwio, int kh, int kw, int64_t cin, int64_t cout, uint16_t* fwd_hi, uint16_t* fwd_lo,
-                                 int64_t fwd_ld, uint16_t* dgrad_hi, uint16_t* dgrad_lo, int64_t dgrad_ld, int64_t dgrad_tap,
+                                 int64_t fwd_ld, int64_t fwd_rs, uint16_t* dgrad_hi, uint16_t* dgrad_lo, int64_t dgrad_ld, int64_t dgrad_tap,
                                  void* stream);
 /* split-output / split-input variants of the streaming kernels below (same arithmetic, activations in split planes) */
 int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean, const float* rstd, float eps,
                            const float* beta, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, int flags, void* stream);
+/* same contract as ds_bn_relu_bwd_reduce; column-fixed row-streaming schedule used by the product path */
+int ds_bn_relu_bwd_reduce2(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean,
+                           const float* rstd, const float* beta, double* sums, int64_t sums_ld, void* stream);
 int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
                                const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
+/* sums[c] += sum_rows dy[row,c] * [y[row,c] > 0] on a max-pooled map: the beta gradient of a frozen conv+BN+ReLU whose only
+ * consumer is that max pool (the stem, image_model/inception_v1.py:63-67), without differentiating through the pool */
+int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldy, int64_t m, int64_t n,
+                           double* sums, void* stream);
 /* dbeta[c] = sums[c] (the frozen stem needs no dz: only its beta gradient) */
 int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream);
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,

@@ -38,65 +38,172 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint16_t* __restrict__
 }
 
 // ---- batch norm ----------------------------------------------------------------------------------------------------
-// y = relu((z - mean) * rstd + beta) -> split planes.  2-D launch: blockIdx.y strides rows, x covers column groups.
-__global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int ncg,
+// Column-fixed row streaming: blockDim = (cgs, rl); a thread owns one group of 4 channels (its per-channel parameters live in
+// registers) and walks rows r0 + ty, += rl with 4 independent rows in flight - no per-element index arithmetic.
+struct RowGrid { dim3 grid, block; int rows_per_cta; };
+RowGrid row_grid(int64_t M, int64_t N, int ctas_per_sm, int min_rows = 0) {
+  const int ncg = (int)(N / 4);
+  int best = std::min(ncg, 32);
+  double best_util = 0.0;
+  for (int c = std::min(ncg, 32); c >= std::min(ncg, 8); --c) {      // widest x-extent with the fewest idle lanes
+    const double util = (double)ncg / (double)(ds::cdiv(ncg, c) * c);
+    if (util > best_util + 1e-9) { best_util = util; best = c; }
+  }
+  RowGrid g;
+  g.block = dim3(best, 256 / best);
+  const unsigned gx = (unsigned)ds::cdiv(ncg, best);
+  int64_t rows = ds::cdiv(M, std::max<int64_t>(1, (148 * ctas_per_sm) / gx));
+  rows = std::max<int64_t>(rows, min_rows);
+  rows = std::max<int64_t>(4 * g.block.y, ds::cdiv(rows, 4 * g.block.y) * 4 * g.block.y);
+  g.rows_per_cta = (int)rows;
+  g.grid = dim3(gx, (unsigned)ds::cdiv(M, rows));
+  return g;
+}
+
+// y = relu((z - mean) * rstd + beta) -> split planes
+__global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              float eps, const float* __restrict__ beta,
                                                              uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
-                                                             int64_t ldy, int flags) {
-  const bool use_var = (flags & DS_BN_USE_VAR) != 0;
+                                                             int64_t ldy, int flags, int rows_per_cta) {
+  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= N) return;
   const bool relu = !(flags & DS_BN_NO_RELU);
-  const uint32_t total = (uint32_t)(M * ncg);       // host guarantees < 2^31
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t r = i / (uint32_t)ncg;
-    const int col = (int)(i - r * (uint32_t)ncg) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(z + (int64_t)r * ldz + col);
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + col));
-    float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + col));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + col));
-    if (use_var) { rs.x = rsqrtf(rs.x + eps); rs.y = rsqrtf(rs.y + eps); rs.z = rsqrtf(rs.z + eps); rs.w = rsqrtf(rs.w + eps); }
-    float out[4] = {(v.x - mu.x) * rs.x + be.x, (v.y - mu.y) * rs.y + be.y, (v.z - mu.z) * rs.z + be.z,
-                    (v.w - mu.w) * rs.w + be.w};
-    if (relu) {
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + col));
+  float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + col));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + col));
+  if (flags & DS_BN_USE_VAR) { rs.x = rsqrtf(rs.x + eps); rs.y = rsqrtf(rs.y + eps); rs.z = rsqrtf(rs.z + eps); rs.w = rsqrtf(rs.w + eps); }
+  const int rl = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  for (int64_t rb = r0 + threadIdx.y; rb < r1; rb += 4 * rl) {
+    float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = fmaxf(out[j], 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * rl;
+      if (r < r1) v[u] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
     }
-    ds::store4_split(y_hi + (int64_t)r * ldy + col, y_lo + (int64_t)r * ldy + col, out);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * rl;
+      if (r < r1) {
+        float out[4] = {(v[u].x - mu.x) * rs.x + be.x, (v[u].y - mu.y) * rs.y + be.y, (v[u].z - mu.z) * rs.z + be.z,
+                        (v[u].w - mu.w) * rs.w + be.w};
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[j] = fmaxf(out[j], 0.f);
+        }
+        ds::store4_split(y_hi + r * ldy + col, y_lo + r * ldy + col, out);
+      }
+    }
+  }
+}
+
+// g = dy * [bn(z) > 0]; sums[c] += sum g, sums[sums_ld + c] += sum g * xhat
+__global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z,
+                                                             int64_t ldz, int64_t M, int64_t N, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                             double* __restrict__ sums, int64_t sums_ld, int rows_per_cta) {
+  const int cgs = blockDim.x, rl = blockDim.y;
+  const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (col < N) {
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    for (int64_t rb = r0 + threadIdx.y; rb < r1; rb += 4 * rl) {
+      float4 zv[4], gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = rb + (int64_t)u * rl;
+        if (r < r1) {
+          zv[u] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
+          gv[u] = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
+        } else {
+          zv[u] = make_float4(0.f, 0.f, 0.f, 0.f); gv[u] = zv[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (zz[j] - mu[j]) * rs[j];
+          const float g = (xh + be[j] > 0.f) ? gg[j] : 0.f;
+          s[j] += g;
+          q[j] = fmaf(g, xh, q[j]);
+        }
+      }
+    }
+  }
+  __shared__ float red[256 * 8];
+  const int t = threadIdx.y * cgs + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red[t * 8 + i] = s[i]; red[t * 8 + 4 + i] = q[i]; }
+  __syncthreads();
+  // 8 values per column group (4 x sum g, 4 x sum g*xhat): thread (tx, ty < 8) folds value ty over the row lanes
+  if (col < N) {
+    for (int v = threadIdx.y; v < 8; v += rl) {
+      double a = 0.0;
+      for (int y = 0; y < rl; ++y) a += red[(y * cgs + threadIdx.x) * 8 + v];
+      atomicAdd(sums + (v < 4 ? 0 : sums_ld) + col + (v & 3), a);
+    }
   }
 }
 
 // dz = rstd * (g - sum(g)/m - xhat * sum(g*xhat)/m), g = dy * [bn(z) > 0]  -> split planes (z is left untouched)
 __global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __restrict__ dy, int64_t lddy,
-                                                                 const float* __restrict__ z, int64_t ldz, int64_t M, int N,
+                                                                 const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ beta, const double* __restrict__ sums,
                                                                  int64_t sums_ld, uint16_t* __restrict__ dz_hi,
-                                                                 uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta) {
-  const int ncg = N >> 2;
-  const uint32_t total = (uint32_t)(M * ncg);
+                                                                 uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
+                                                                 int rows_per_cta) {
+  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= N) return;
   const double inv_m = 1.0 / (double)M;
-  if (blockIdx.x == 0 && dbeta) {
-    for (int col = threadIdx.x; col < N; col += blockDim.x) dbeta[col] = (float)sums[col];
-  }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t r = i / (uint32_t)ncg;
-    const int col = (int)(i - r * (uint32_t)ncg) * 4;
-    const float4 zv = *reinterpret_cast<const float4*>(z + (int64_t)r * ldz + col);
-    const float4 gv = *reinterpret_cast<const float4*>(dy + (int64_t)r * lddy + col);
-    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
-    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
-    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
-    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
-    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
-    float out[4];
+  const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+  const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float m1[4], m2[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xh = (zz[j] - mu[j]) * rs[j];
-      const float g = (xh + be[j] > 0.f) ? gg[j] : 0.f;
-      const float m1 = (float)(sums[col + j] * inv_m), m2 = (float)(sums[sums_ld + col + j] * inv_m);
-      out[j] = rs[j] * (g - m1 - xh * m2);
+  for (int j = 0; j < 4; ++j) {
+    m1[j] = (float)(sums[col + j] * inv_m);
+    m2[j] = (float)(sums[sums_ld + col + j] * inv_m);
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0 && dbeta) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dbeta[col + j] = (float)sums[col + j];
+  }
+  const int rl = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  for (int64_t rb = r0 + threadIdx.y; rb < r1; rb += 4 * rl) {
+    float4 zv[4], gv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * rl;
+      if (r < r1) {
+        zv[u] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
+        gv[u] = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
+      }
     }
-    ds::store4_split(dz_hi + (int64_t)r * lddz + col, dz_lo + (int64_t)r * lddz + col, out);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * rl;
+      if (r < r1) {
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (zz[j] - mu[j]) * rs[j];
+          const float g = (xh + be[j] > 0.f) ? gg[j] : 0.f;
+          out[j] = rs[j] * (g - m1[j] - xh * m2[j]);
+        }
+        ds::store4_split(dz_hi + r * lddz + col, dz_lo + r * lddz + col, out);
+      }
+    }
   }
 }
 
@@ -228,52 +335,89 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
 }
 
 // Explicit im2col of a small-Cin strided convolution (the 7x7/2 stem, image_model/inception_v1.py:63) into the split-bf16
-// GEMM operand: out[m, (r*kw + s)*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c] (0 outside), K padded
-// with zeros to k8 = roundup(kh*kw*cin, 8).  One thread per (output pixel, 8 consecutive K entries): 16-byte stores.
-template <int CIN_T, int KW_T>   // 0 = runtime value
-__global__ void __launch_bounds__(256) im2col_small_cin_kernel(const float* __restrict__ x, int64_t m_begin, int64_t m_count, int h, int w,
-                                                               int cin_rt, int kh, int kw_rt, int stride, int pad_t, int pad_l, int ho,
-                                                               int wo, uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
-                                                               int64_t ldo, int k8) {
-  const int cin = CIN_T ? CIN_T : cin_rt, kw = KW_T ? KW_T : kw_rt;
-  const int groups = k8 >> 3;
-  const int K = kh * kw * cin;
-  const int64_t total = m_count * groups;
+// GEMM operand.  K layout: kh groups of kg = roundup(kw*cin, 8) entries, group r = [x[ih0 + r, iw0 .. iw0 + kw - 1, 0..cin-1] | 0 pad]
+// - one filter row is a contiguous run of kw*cin floats in the NHWC image, and a group is whole 16-byte stores.
+// One thread per (output pixel, filter row).
+template <int CIN, int KW>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restrict__ x, int64_t m_begin, int64_t m_count, int h, int w,
+                                                          int kh, int stride, int pad_t, int pad_l, int ho, int wo,
+                                                          uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int64_t ldo) {
+  constexpr int RUN = KW * CIN, KG = (RUN + 7) / 8 * 8;
+  const int64_t total = m_count * kh;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const int64_t ml = i / groups;
+    const int r = (int)(i % kh);
+    const int64_t ml = i / kh;
     const int64_t m = m_begin + ml;
     const int q = (int)(m % wo);
     const int64_t t2 = m / wo;
     const int p = (int)(t2 % ho);
     const int64_t b = t2 / ho;
-    const int ih0 = p * stride - pad_t, iw0 = q * stride - pad_l;
-    const float* xb = x + b * (int64_t)h * w * cin;
-    uint32_t hh[8], ll[8];
+    const int ih = p * stride - pad_t + r, iw0 = q * stride - pad_l;
+    const bool row_ok = ih >= 0 && ih < h;
+    const float* src = x + ((b * h + (row_ok ? ih : 0)) * (int64_t)w + iw0) * CIN;
+    uint32_t hh[KG], ll[KG];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
+    for (int j = 0; j < KG; ++j) {
       float v = 0.f;
-      if (k < K) {
-        const int c = k % cin;
-        const int t = k / cin;
-        const int s = t % kw, r = t / kw;
-        const int ih = ih0 + r, iw = iw0 + s;
-        if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(xb + ((int64_t)ih * w + iw) * cin + c);
+      if (j < RUN) {
+        const int iw = iw0 + j / CIN;
+        if (row_ok && iw >= 0 && iw < w) v = __ldg(src + j);
       }
       ds::split_bf16(v, hh[j], ll[j]);
     }
-    const int64_t o = ml * ldo + g * 8;
-    *reinterpret_cast<uint4*>(o_hi + o) = make_uint4(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16), hh[4] | (hh[5] << 16), hh[6] | (hh[7] << 16));
-    *reinterpret_cast<uint4*>(o_lo + o) = make_uint4(ll[0] | (ll[1] << 16), ll[2] | (ll[3] << 16), ll[4] | (ll[5] << 16), ll[6] | (ll[7] << 16));
+    const int64_t o = ml * ldo + r * KG;
+#pragma unroll
+    for (int j = 0; j < KG; j += 8) {
+      *reinterpret_cast<uint4*>(o_hi + o + j) =
+          make_uint4(hh[j] | (hh[j + 1] << 16), hh[j + 2] | (hh[j + 3] << 16), hh[j + 4] | (hh[j + 5] << 16), hh[j + 6] | (hh[j + 7] << 16));
+      *reinterpret_cast<uint4*>(o_lo + o + j) =
+          make_uint4(ll[j] | (ll[j + 1] << 16), ll[j + 2] | (ll[j + 3] << 16), ll[j + 4] | (ll[j + 5] << 16), ll[j + 6] | (ll[j + 7] << 16));
+    }
   }
 }
 
-// HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld) and input-gradient operand [cin][kh'][kw'][cout]
-// (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout so that sibling 1x1 convs can share one fused operand),
+// sums[c] += sum_rows dy[row, c] * [y[row, c] > 0]: the beta gradient of a frozen conv + BN + ReLU whose only consumer is a max
+// pool, read off the *pooled* map (a pooled value is > 0 exactly when the element it was taken from passed the ReLU, and each
+// pool output routes its gradient to exactly one element) - no need to differentiate through the pool (the stem).
+__global__ void __launch_bounds__(256) masked_colsum_split_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                                  const uint16_t* __restrict__ y_hi, const uint16_t* __restrict__ y_lo,
+                                                                  int64_t ldy, int64_t M, int64_t N, double* __restrict__ sums,
+                                                                  int rows_per_cta) {
+  const int cgs = blockDim.x, rl = blockDim.y;
+  const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  float s[4] = {0, 0, 0, 0};
+  if (col < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += rl) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
+      float yv[4];
+      ds::load4_split(y_hi + r * ldy + col, y_lo + r * ldy + col, yv);
+      s[0] += yv[0] > 0.f ? g.x : 0.f; s[1] += yv[1] > 0.f ? g.y : 0.f;
+      s[2] += yv[2] > 0.f ? g.z : 0.f; s[3] += yv[3] > 0.f ? g.w : 0.f;
+    }
+  }
+  __shared__ float red[256 * 4];
+  const int t = threadIdx.y * cgs + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[t * 4 + i] = s[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    double a[4] = {0, 0, 0, 0};
+    for (int y = 0; y < rl; ++y)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] += red[(y * cgs + threadIdx.x) * 4 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(sums + col + i, a[i]);
+  }
+}
+
+// HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld, filter-row stride fwd_rs >= kw*cin) and input-gradient
+// operand [cin][kh'][kw'][cout] (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout so that sibling 1x1 convs can share one fused operand),
 // each as hi / lo bf16 planes
 __global__ void repack_split_kernel(const float* __restrict__ hwio, int kh, int kw, int64_t cin, int64_t cout,
-                                    uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, int64_t fwd_ld,
+                                    uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, int64_t fwd_ld, int64_t fwd_rs,
                                     uint16_t* __restrict__ d_hi, uint16_t* __restrict__ d_lo, int64_t dgrad_ld,
                                     int64_t dgrad_tap) {
   const int64_t total = (int64_t)kh * kw * cin * cout;
@@ -284,7 +428,7 @@ __global__ void repack_split_kernel(const float* __restrict__ hwio, int kh, int 
     uint32_t h, l;
     ds::split_bf16(hwio[i], h, l);
     if (f_hi) {
-      const int64_t o = co * fwd_ld + ((int64_t)r * kw + s) * cin + ci;
+      const int64_t o = co * fwd_ld + (int64_t)r * fwd_rs + (int64_t)s * cin + ci;
       f_hi[o] = (uint16_t)h; f_lo[o] = (uint16_t)l;
     }
     if (d_hi) {
@@ -320,10 +464,9 @@ int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, co
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z) & 15) == 0, "16-byte alignment");
   DS_REQUIRE((((uintptr_t)y_hi | (uintptr_t)y_lo) & 7) == 0, "8-byte aligned planes");
-  DS_REQUIRE(m * (n / 4) < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (m == 0 || n == 0) return 0;
-  bn_apply_split_kernel<<<ew_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(z, ldz, m, (int)(n / 4), mean, rstd, eps, beta, y_hi, y_lo,
-                                                                         ldy, flags);
+  const RowGrid g = row_grid(m, n, 16);
+  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, g.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -333,10 +476,21 @@ int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, in
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream) {
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0 && lddz % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dy) & 15) == 0, "16-byte alignment");
-  DS_REQUIRE(m * (n / 4) < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (m == 0 || n == 0) return 0;
-  bn_bwd_apply_split_kernel<<<ew_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, (int)n, mean, rstd, beta, sums,
-                                                                             sums_ld, dz_hi, dz_lo, lddz, dbeta);
+  const RowGrid g = row_grid(m, n, 16);
+  bn_bwd_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo,
+                                                                 lddz, dbeta, g.rows_per_cta);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_relu_bwd_reduce2(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean,
+                           const float* rstd, const float* beta, double* sums, int64_t sums_ld, void* stream) {
+  DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
+  DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dy) & 15) == 0, "16-byte alignment");
+  if (m == 0 || n == 0) return 0;
+  const RowGrid g = row_grid(m, n, 6, 128);
+  bn_bwd_reduce2_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, g.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -393,31 +547,43 @@ int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_
 int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
                               int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
                               uint16_t* o_lo, int64_t ldo, void* stream) {
-  const int k8 = (int)((kh * kw * cin + 7) / 8 * 8);
-  DS_REQUIRE(ldo % 8 == 0 && ldo >= k8, "output row stride must be a multiple of 8 and cover the padded K");
+  DS_REQUIRE(cin == 3 && kw == 7, "ds_im2col_small_cin_split is specialised for the 7x7x3 stem (image_model/inception_v1.py:63)");
+  const int kg = (int)((kw * cin + 7) / 8 * 8);
+  DS_REQUIRE(ldo % 8 == 0 && ldo >= (int64_t)kh * kg, "output row stride must be a multiple of 8 and cover kh * roundup(kw*cin, 8)");
   DS_REQUIRE((((uintptr_t)o_hi | (uintptr_t)o_lo) & 15) == 0, "16-byte aligned planes");
   DS_REQUIRE(m_begin >= 0 && m_begin + m_count <= batch * ho * wo, "row range outside the output");
   if (m_count == 0) return 0;
-  if (cin == 3 && kw == 7)
-    im2col_small_cin_kernel<3, 7><<<ew_blocks(m_count * (k8 / 8)), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, (int)cin, kh,
-                                                                                          kw, stride, pad_t, pad_l, (int)ho, (int)wo, o_hi,
-                                                                                          o_lo, ldo, k8);
-  else
-    im2col_small_cin_kernel<0, 0><<<ew_blocks(m_count * (k8 / 8)), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, (int)cin, kh,
-                                                                                          kw, stride, pad_t, pad_l, (int)ho, (int)wo, o_hi,
-                                                                                          o_lo, ldo, k8);
+  im2col_rows_kernel<3, 7><<<ew_blocks(m_count * kh), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, kh, stride, pad_t, pad_l,
+                                                                             (int)ho, (int)wo, o_hi, o_lo, ldo);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldy, int64_t m, int64_t n,
+                           double* sums, void* stream) {
+  DS_REQUIRE(n % 4 == 0 && lddy % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
+  if (m == 0 || n == 0) return 0;
+  int cgs = (int)std::min<int64_t>(n / 4, 32), pw = 1;
+  while (pw * 2 <= cgs) pw *= 2;
+  const dim3 blk(pw, 256 / pw);
+  const unsigned gx = (unsigned)ds::cdiv(n / 4, blk.x);
+  int64_t rows = ds::cdiv(m, std::max<int64_t>(1, (148 * 24) / gx));
+  rows = std::max<int64_t>(256, ds::cdiv(rows, 64) * 64);
+  dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
+  masked_colsum_split_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, y_hi, y_lo, ldy, m, n, sums, (int)rows);
   DS_LAUNCH_CHECK();
   return 0;
 }
 
 int ds_repack_conv_weights_split(const float* hwio, int kh, int kw, int64_t cin, int64_t cout, uint16_t* fwd_hi, uint16_t* fwd_lo,
-                                 int64_t fwd_ld, uint16_t* dgrad_hi, uint16_t* dgrad_lo, int64_t dgrad_ld, int64_t dgrad_tap,
+                                 int64_t fwd_ld, int64_t fwd_rs, uint16_t* dgrad_hi, uint16_t* dgrad_lo, int64_t dgrad_ld, int64_t dgrad_tap,
                                  void* stream) {
   const int64_t total = (int64_t)kh * kw * cin * cout;
   if (total == 0) return 0;
   DS_REQUIRE((fwd_hi == nullptr) == (fwd_lo == nullptr) && (dgrad_hi == nullptr) == (dgrad_lo == nullptr), "planes go in pairs");
   const int blocks = (int)std::min<int64_t>(ds::cdiv(total, 256), 148 * 8);
-  repack_split_kernel<<<blocks, 256, 0, ds::S(stream)>>>(hwio, kh, kw, cin, cout, fwd_hi, fwd_lo, fwd_ld, dgrad_hi, dgrad_lo, dgrad_ld,
+  repack_split_kernel<<<blocks, 256, 0, ds::S(stream)>>>(hwio, kh, kw, cin, cout, fwd_hi, fwd_lo, fwd_ld, fwd_rs > 0 ? fwd_rs : kw * cin,
+                                                         dgrad_hi, dgrad_lo, dgrad_ld,
                                                          dgrad_tap);
   DS_LAUNCH_CHECK();
   return 0;

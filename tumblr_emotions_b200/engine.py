@@ -57,6 +57,7 @@ class ConvUnit:
         self.M = eng.batch * self.h_out * self.h_out
         self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
         self.split = eng.split
+        self.dbeta_pool = None
         self.tc = self.split and stride == 1 and k in (1, 3) and cin % 8 == 0
         self.Z = eng.new(self.M, self.N)
         off = eng.bn_cursor
@@ -76,8 +77,9 @@ class ConvUnit:
             self.w_fwd = SView(eng.new_split((self.N,), kk * cin))           # [N][r][s][cin]
             self.w_dgrad = SView(eng.new_split((cin,), kk * self.N))         # [cin][r'][s'][N]
         elif self.stem_tc:
-            self.k8 = (kk * cin + 7) // 8 * 8
-            self.w_fwd = SView(eng.new_split((self.N,), self.k8))            # [N][(r,s,c) zero-padded to k8]
+            self.kg = (k * cin + 7) // 8 * 8                                 # one filter row = a zero-padded group of 16-byte stores
+            self.k8 = k * self.kg
+            self.w_fwd = SView(eng.new_split((self.N,), self.k8))            # [N][r][(s,c) zero-padded to kg]
             self.w_dgrad = None
             self.chunk_imgs = min(eng.batch, 16)                             # 16 images x 12544 pixels x 608 B = 122 MB ~ L2
             self.col = SView(eng.new_split((self.chunk_imgs * self.h_out * self.h_out,), self.k8))
@@ -100,7 +102,7 @@ class ConvUnit:
             if self.tc:
                 ops.repack_conv_weights_split(w, fwd=self.w_fwd.rows_slice(c, n), dgrad=self.w_dgrad.slice(c, n), dgrad_tap=self.N)
             elif self.stem_tc:
-                ops.repack_conv_weights_split(w, fwd=self.w_fwd)
+                ops.repack_conv_weights_split(w, fwd=self.w_fwd, fwd_rs=self.kg)
             else:
                 ops.repack_conv_weights(w, fwd=None, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
                                         round_tf32=False)
@@ -154,9 +156,13 @@ class ConvUnit:
     def bwd(self):
         e, B, h = self.eng, self.eng.batch, self.h_out
         Zv = View(self.Z)
+        if self.dbeta_pool is not None:      # frozen conv feeding only a max pool: beta gradient straight from the pooled map
+            ops.masked_colsum_split(self.dbeta_pool.dy, self.dbeta_pool.y, self.sums)
+            ops.bn_dbeta(self.sums, self.N, self.dbeta)
+            return
         for (c, n), dy in zip(self.segs, self.douts):
             ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
-                                   self.N)
+                                   self.N, fast=self.split)
         if self.dx is None and not self.trainable:      # frozen stem: only its beta gradient is needed
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
@@ -208,15 +214,18 @@ class PoolNode:
         self.eng, self.k, self.stride, self.c, self.h_in = eng, k, stride, c, h_in
         self.h_out, self.pad, _ = same_pad(h_in, k, stride)
         self.x, self.y, self.dx, self.dy, self.dx_accumulate = x, y, dx, dy, dx_accumulate
+        self.skip_bwd = False           # set when the producer takes its beta gradient from the pooled map instead
         self.argmax = torch.empty(eng.batch * self.h_out * self.h_out * c, dtype=torch.uint8, device=eng.device)
 
     def fwd(self, train):
         B = self.eng.batch
         f = ops.maxpool_fwd_split if self.eng.split else ops.maxpool_fwd
         f(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out, self.y,
-          self.argmax if train else None)
+          self.argmax if (train and not self.skip_bwd) else None)
 
     def bwd(self):
+        if self.skip_bwd:
+            return
         B = self.eng.batch
         ops.maxpool_bwd(self.dy, self.argmax, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
                         self.h_out, self.dx, self.dx_accumulate)
@@ -328,7 +337,11 @@ class Engine:
                 ho = same_pad(h, k, s)[0]
                 _, vout = self.act(B, ho, ho, c)
                 dout = self.new(B, ho, ho, c) if tr else None
-                self.nodes.append(PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None))
+                node = PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None)
+                prev = self.nodes[-1] if self.nodes else None
+                if tr and self.split and isinstance(prev, ConvUnit) and prev.dx is None and not prev.trainable:
+                    prev.dbeta_pool, node.skip_bwd = node, True
+                self.nodes.append(node)
                 act, dact, h = vout, View(dout) if tr else None, ho
             else:
                 c0, c1a, c1b, c2a, c2b, c3, _ = MIXED[name]

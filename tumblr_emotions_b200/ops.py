@@ -132,11 +132,15 @@ def im2col_small_cin_split(x: torch.Tensor, batch, h, w, cin, kh, kw, stride, pa
                                  out.lo_ptr, out.ld, _stream())
 
 
-def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None):
+def masked_colsum_split(dy: View, y: SView, sums):
+    lib().masked_colsum_split(dy.ptr, dy.ld, y.ptr, y.lo_ptr, y.ld, y.rows, y.cols, _p(sums), _stream())
+
+
+def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None, fwd_rs: int = 0):
     """dgrad: SView over the [cin, kh*kw*dgrad_tap] operand, already sliced to this conv's channel offset"""
     kh, kw, cin, cout = hwio.shape
     lib().repack_conv_weights_split(hwio.data_ptr(), kh, kw, cin, cout, fwd.ptr if fwd else 0, fwd.lo_ptr if fwd else 0,
-                                    fwd.ld if fwd else 0, dgrad.ptr if dgrad else 0, dgrad.lo_ptr if dgrad else 0,
+                                    fwd.ld if fwd else 0, fwd_rs, dgrad.ptr if dgrad else 0, dgrad.lo_ptr if dgrad else 0,
                                     dgrad.ld if dgrad else 0, dgrad_tap if dgrad_tap is not None else cout, _stream())
 
 
@@ -224,8 +228,8 @@ def bn_apply_relu(z: View, mean, rstd, eps, beta, y: View, flags=0):
     lib().bn_apply_relu(z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), eps, _p(beta), y.ptr, y.ld, flags, _stream())
 
 
-def bn_relu_bwd_reduce(dy: View, z: View, mean, rstd, beta, sums, sums_ld):
-    lib().bn_relu_bwd_reduce(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
+def bn_relu_bwd_reduce(dy: View, z: View, mean, rstd, beta, sums, sums_ld, fast=False):
+    (lib().bn_relu_bwd_reduce2 if fast else lib().bn_relu_bwd_reduce)(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
                              _stream())
 
 
