@@ -161,11 +161,23 @@ class _Model:
         """W_embedding.assign(embedding_placeholder) (im_text_rnn_model.py:83-84, run at step 0 :150-151)"""
         self.engine.load_state_dict({"Text/W_embedding": torch.as_tensor(self.embedding, dtype=torch.float32)}, strict=False)
 
-    def feed(self, batch: Dict[str, torch.Tensor]):
+    def _inputs(self, batch):
         e = self.engine
-        e.set_batch(batch.get("images") if e.has_image else None, batch.get("ids") if e.has_text else None,
-                    batch.get("seq_lens") if e.has_text else None, batch["labels"])
+        return (batch.get("images") if e.has_image else None, batch.get("ids") if e.has_text else None,
+                batch.get("seq_lens") if e.has_text else None, batch["labels"])
+
+    def feed(self, batch: Dict[str, torch.Tensor]):
+        self.engine.set_batch(*self._inputs(batch))
         self.post_ids, self.days = batch.get("post_ids"), batch.get("days")
+
+    def prefetch(self, batch: Dict[str, torch.Tensor]):
+        """start the H2D copy of the next batch on the copy stream (overlaps the step in flight)"""
+        self.engine.prefetch(*self._inputs(batch))
+        self._next_meta = (batch.get("post_ids"), batch.get("days"))
+
+    def commit_prefetch(self):
+        self.engine.commit_prefetch()
+        self.post_ids, self.days = self._next_meta
 
 
 class DeepSentiment(_Model):
@@ -220,12 +232,16 @@ def _train(model_cls, config, checkpoints_dir, train_dir, num_steps, use_init_fn
             epoch += 1
         if step == 0 and model.kind != "image":
             model.embedding_init()
-        model.feed(model.dataset.next_batch(batch_size))
+        if step == 0:
+            model.prefetch(model.dataset.next_batch(batch_size))
+        model.commit_prefetch()
         if use_graph:
             eng.train_step_graph(model.learning_rate)
         else:
             eng.train_step(model.learning_rate, allreduce)
         step += 1
+        if step < num_steps:                  # the next batch's host->device copy overlaps this step's kernels
+            model.prefetch(model.dataset.next_batch(batch_size))
         if log_every and step % log_every == 0 or step == num_steps:
             total_loss = eng.total_loss()
             if rank == 0 and log_every:

@@ -786,6 +786,33 @@ class Engine:
             self._g2.replay()
         self.adam_t += 1
 
+    # -- input pipeline ---------------------------------------------------------------------------------------
+    def prefetch(self, images=None, ids=None, seq_lens=None, labels=None):
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream into staging buffers, so
+        that it overlaps the step in flight; `commit_prefetch()` then moves it into the step's static input buffers with
+        device-to-device copies on the compute stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage, self._stage_evt = {}, torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            for name, src in (("images", images), ("ids", ids), ("seq_lens", seq_lens), ("labels", labels)):
+                if src is None:
+                    continue
+                dst = getattr(self, name)
+                if name not in self._stage:
+                    self._stage[name] = torch.empty_like(dst)
+                self._stage[name].copy_(src, non_blocking=True)
+            self._stage_evt.record(self._copy_stream)
+        self._staged = [n for n, v in (("images", images), ("ids", ids), ("seq_lens", seq_lens), ("labels", labels)) if v is not None]
+
+    def commit_prefetch(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_evt)
+        for name in self._staged:
+            getattr(self, name).copy_(self._stage[name], non_blocking=True)
+        # the staging buffers may be overwritten by the next prefetch only after these copies ran
+        self._copy_stream.wait_stream(cur)
+
     # -- convenience -----------------------------------------------------------------------------------------
     def set_batch(self, images=None, ids=None, seq_lens=None, labels=None):
         if images is not None:
