@@ -48,6 +48,16 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_bf16x3_kernel launch, from the committed ncu pass over one joint
+    training step at batch 256 (profiles/r01_conv_traffic.json; the number is a profile artefact, not measured in this run)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """samples nvidia-smi SM clocks / throttle reasons while the timed region runs"""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -260,7 +270,7 @@ def run_ours(args):
                                       "that on the bf16 tensor pipe (frac_issued)" % (src, pk["bf16_tflops_sustained"]),
                          "frac_issued": roof["issued_tflops"] / peak,
                          "mixed4_frac_issued": (roof["mixed4_issued_tflops"] / peak) if roof["mixed4_issued_tflops"] else None,
-                         "traffic": None})
+                         "traffic": conv_traffic()})
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -281,7 +291,10 @@ def kernel_pass(eng, ops, lr):
         s.record()
         orig(a, batch, h, w, cin, ksize, bt, n, c, *rest, **kw)
         e.record()
-        recs.append((s, e, 2.0 * batch * h * w * ksize * ksize * cin * n, (batch * h * w, ksize * ksize * cin, n, ksize)))
+        flags = kw.get("flags", 0)
+        # algorithmic bytes: A and B read once (4 bytes per split value), C written once (read too by the accumulate epilogue)
+        nbytes = 4.0 * (batch * h * w * cin + n * ksize * ksize * cin + batch * h * w * n * (2 if flags & ops.EPI_ACCUMULATE else 1))
+        recs.append((s, e, 2.0 * batch * h * w * ksize * ksize * cin * n, (batch * h * w, ksize * ksize * cin, n, ksize), nbytes))
 
     ops.conv_bf16x3 = timed
     try:
@@ -291,14 +304,16 @@ def kernel_pass(eng, ops, lr):
         torch.cuda.synchronize()
     finally:
         ops.conv_bf16x3 = orig
-    tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
-    tot_fl = sum(f for _, _, f, _ in recs)
+    tot_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+    tot_fl = sum(r[2] for r in recs)
+    tot_bytes = sum(r[4] for r in recs)
     # Mixed_4b-4f contractions: 14x14 spatial -> M = batch*196
-    m4 = [(s.elapsed_time(e), f) for s, e, f, shp in recs if shp[0] == eng.batch * 196]
+    m4 = [(r[0].elapsed_time(r[1]), r[2]) for r in recs if r[3][0] == eng.batch * 196]
     m4_ms, m4_fl = sum(x for x, _ in m4), sum(f for _, f in m4)
     return {"kernel": "conv_bf16x3_kernel (persistent tcgen05 split-bf16 implicit GEMM: 1x1/3x3 conv fwd + dgrad + wgrad, LSTM GEMMs)",
             "achieved": tot_fl / tot_ms / 1e9, "launches": len(recs), "avg_launch_ms": tot_ms / max(len(recs), 1),
             "kernel_ms_per_step": tot_ms, "algorithmic_gflop_per_step": tot_fl / 1e9,
+            "algorithmic_bytes_per_launch": tot_bytes / max(len(recs), 1), "algorithmic_gflop_per_launch": tot_fl / 1e9 / max(len(recs), 1),
             "issued_tflops": 3.0 * tot_fl / tot_ms / 1e9,
             "mixed4_achieved_tflops": (m4_fl / m4_ms / 1e9) if m4_ms else None,
             "mixed4_issued_tflops": (3.0 * m4_fl / m4_ms / 1e9) if m4_ms else None, "mixed4_launches": len(m4)}

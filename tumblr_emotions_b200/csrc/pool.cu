@@ -40,56 +40,71 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
 }
 
 // gather formulation: every input pixel sums the dy of the windows whose recorded argmax is this pixel (deterministic).
-// The (at most NW x NW) candidate windows are fully unrolled: all argmax words are fetched first, dy is only fetched for the
-// windows that actually selected this pixel in one of the thread's 4 channels.
-template <int K, int S>
+// A thread owns one input pixel x G groups of 4 channels.  The (at most NW x NW) candidate windows are fully unrolled; per
+// window the G argmax words are compared bytewise (__vcmpeq4) and dy is only fetched for the words that selected this pixel.
+template <int K, int S, int G>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, int64_t lddy,
-                                                          const uint8_t* __restrict__ argmax, int64_t B, int h, int w, int c4,
+                                                          const uint8_t* __restrict__ argmax, int64_t B, int h, int w, int cg_n,
                                                           int pad_t, int pad_l, int ho, int wo,
                                                           float* __restrict__ dx, int64_t lddx, int accumulate) {
   constexpr int NW = (K + S - 1) / S;
+  const int c4 = cg_n * G;                              // float4 groups per pixel
   // one CTA per input row (b, ih): a single 32-bit division per work item instead of a div/mod chain
   const int64_t b = blockIdx.x / (uint32_t)h;
   const int ih = (int)(blockIdx.x - b * h);
-  const uint32_t row_items = (uint32_t)w * (uint32_t)c4;
+  const uint32_t row_items = (uint32_t)w * (uint32_t)cg_n;
   for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
-    const int iw = (int)(i / (uint32_t)c4);
-    const int cg = (int)(i - (uint32_t)iw * (uint32_t)c4);
+    const int iw = (int)(i / (uint32_t)cg_n);
+    const int cg = (int)(i - (uint32_t)iw * (uint32_t)cg_n) * G;       // first float4 group of this thread
     const int p_hi = (ih + pad_t) / S, q_hi = (iw + pad_l) / S;
-    uint32_t am[NW * NW];
-    uint32_t me[NW * NW];
+    // phase 1: the argmax words of every candidate window (independent loads), turned into per-byte match masks
+    uint32_t mk[NW * NW][G];
     int64_t oo[NW * NW];
 #pragma unroll
     for (int a = 0; a < NW; ++a)
 #pragma unroll
       for (int c = 0; c < NW; ++c) {
+        const int n = a * NW + c;
         const int p = p_hi - a, q = q_hi - c;
         const int r = ih + pad_t - p * S, s = iw + pad_l - q * S;
         const bool v = p >= 0 && p < ho && q >= 0 && q < wo && r < K && s < K;
         const int64_t o = ((b * ho + (v ? p : 0)) * (int64_t)wo + (v ? q : 0));
-        oo[a * NW + c] = o;
-        me[a * NW + c] = v ? (uint32_t)(r * K + s) : 0xffu;      // 0xff never matches a recorded in-window argmax of a valid tap
-        am[a * NW + c] = __ldg(reinterpret_cast<const uint32_t*>(argmax + (o * c4 + cg) * 4));
-      }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        oo[n] = o;
+        const uint32_t me4 = v ? (uint32_t)(r * K + s) * 0x01010101u : 0xfefefefeu;      // 0xfe never equals a recorded tap index
 #pragma unroll
-    for (int n = 0; n < NW * NW; ++n) {
-      const uint32_t m = me[n];
-      if (m == 0xffu) continue;
-      const uint32_t a4 = am[n];
-      const bool m0 = (a4 & 0xffu) == m, m1 = ((a4 >> 8) & 0xffu) == m, m2 = ((a4 >> 16) & 0xffu) == m, m3 = (a4 >> 24) == m;
-      if (m0 | m1 | m2 | m3) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + oo[n] * lddy + cg * 4));
-        if (m0) acc[0] += g.x;
-        if (m1) acc[1] += g.y;
-        if (m2) acc[2] += g.z;
-        if (m3) acc[3] += g.w;
+        for (int g = 0; g < G; ++g)
+          mk[n][g] = __vcmpeq4(__ldg(reinterpret_cast<const uint32_t*>(argmax + (o * c4 + cg + g) * 4)), me4);
       }
+    // phase 2: dy of the windows that selected this pixel (predicated loads, all in flight together); phase 3: masked sums
+    float acc[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { acc[g][0] = 0.f; acc[g][1] = 0.f; acc[g][2] = 0.f; acc[g][3] = 0.f; }
+    float4 gv[NW * NW][G];
+#pragma unroll
+    for (int n = 0; n < NW * NW; ++n)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        gv[n][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mk[n][g]) gv[n][g] = __ldg(reinterpret_cast<const float4*>(dy + oo[n] * lddy + (cg + g) * 4));
+      }
+#pragma unroll
+    for (int n = 0; n < NW * NW; ++n)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t m = mk[n][g];
+        acc[g][0] += (m & 0x000000ffu) ? gv[n][g].x : 0.f;
+        acc[g][1] += (m & 0x0000ff00u) ? gv[n][g].y : 0.f;
+        acc[g][2] += (m & 0x00ff0000u) ? gv[n][g].z : 0.f;
+        acc[g][3] += (m & 0xff000000u) ? gv[n][g].w : 0.f;
+      }
+    float* dst = dx + ((b * h + ih) * (int64_t)w + iw) * lddx + cg * 4;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float4 o4 = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+      float4* d4 = reinterpret_cast<float4*>(dst + g * 4);
+      if (accumulate) { const float4 pz = *d4; o4.x += pz.x; o4.y += pz.y; o4.z += pz.z; o4.w += pz.w; }
+      *d4 = o4;
     }
-    float4* dst = reinterpret_cast<float4*>(dx + ((b * h + ih) * (int64_t)w + iw) * lddx + cg * 4);
-    float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    if (accumulate) { const float4 pz = *dst; o4.x += pz.x; o4.y += pz.y; o4.z += pz.z; o4.w += pz.w; }
-    *dst = o4;
   }
 }
 
@@ -178,9 +193,16 @@ int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t
   if (total == 0) return 0;
   const int blocks = (int)(batch * h);
   DS_REQUIRE(batch * h < (int64_t)1 << 31, "too many rows");
-#define DS_POOL_BWD(KK, SS)                                                                                                   \
-  maxpool_bwd_kernel<KK, SS><<<blocks, 256, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), pad_t, pad_l, \
-                                                               (int)ho, (int)wo, dx, lddx, accumulate)
+  const bool wide = c % 8 == 0;                                          // 8 channels per thread
+#define DS_POOL_BWD(KK, SS)                                                                                                           \
+  do {                                                                                                                                \
+    if (wide)                                                                                                                         \
+      maxpool_bwd_kernel<KK, SS, 2><<<blocks, 128, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 8), pad_t,    \
+                                                                      pad_l, (int)ho, (int)wo, dx, lddx, accumulate);                 \
+    else                                                                                                                              \
+      maxpool_bwd_kernel<KK, SS, 1><<<blocks, 256, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), pad_t,    \
+                                                                      pad_l, (int)ho, (int)wo, dx, lddx, accumulate);                 \
+  } while (0)
   if (k == 3 && stride == 1) DS_POOL_BWD(3, 1);
   else if (k == 3 && stride == 2) DS_POOL_BWD(3, 2);
   else if (k == 2 && stride == 2) DS_POOL_BWD(2, 2);

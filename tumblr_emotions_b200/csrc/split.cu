@@ -242,22 +242,26 @@ __global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* 
         hv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
         lv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
       }
+    // per element: one 32-bit word (hi << 16 | lo) travels with the running maximum; value = float(hi) + float(lo)
     float best[8];
-    uint32_t bh[8], bl[8], arg[8];
+    uint32_t bw[8], arg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0; bl[j] = 0; arg[j] = 255; }
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bw[j] = 0; arg[j] = 255; }
 #pragma unroll
     for (int tp = 0; tp < K * K; ++tp) {
       if (!ok[tp]) continue;
       const uint32_t hw[4] = {hv[tp].x, hv[tp].y, hv[tp].z, hv[tp].w}, lw[4] = {lv[tp].x, lv[tp].y, lv[tp].z, lv[tp].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t hh = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu);
-        const uint32_t ll = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
-        const float v = ds::merge_bf16(hh, ll);
-        if (v > best[j] || arg[j] == 255) { best[j] = v; arg[j] = tp; bh[j] = hh; bl[j] = ll; }
+        // bytes {lo16 of element j, hi16 of element j}: __byte_perm picks them out of the (lo word, hi word) pair
+        const uint32_t wj = __byte_perm(lw[j >> 1], hw[j >> 1], (j & 1) ? 0x7632 : 0x5410);
+        const float v = __uint_as_float(wj & 0xffff0000u) + __uint_as_float(wj << 16);
+        if (v > best[j]) { best[j] = v; bw[j] = wj; arg[j] = tp; }
       }
     }
+    uint32_t bh[8], bl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bh[j] = bw[j] >> 16; bl[j] = bw[j] & 0xffffu; }
     const int64_t o = ((b * ho + p) * (int64_t)wo + q);
     *reinterpret_cast<uint4*>(y_hi + o * ldy + cg * 8) =
         make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
@@ -267,6 +271,91 @@ __global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* 
       *reinterpret_cast<uint2*>(argmax + (o * c8 + cg) * 8) =
           make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24), arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24));
     }
+  }
+}
+
+// 3x3 / stride 1 / pad 1 (the in-block pools): a thread produces a 2x2 patch of outputs for 4 channels from the 4x4 input
+// patch it loads once - 16 tap loads per 4 outputs instead of 36 (the kernel is bound by L1 bandwidth, not HBM).
+// Taps are visited in row-major order, so every output still sees its window in TF scan order (first maximum wins).
+__global__ void __launch_bounds__(128) maxpool3s1_fwd_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
+                                                                   int64_t ldx, int64_t B, int h, int w, int c4,
+                                                                   uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
+                                                                   uint8_t* __restrict__ argmax) {
+  const int ph = (h + 1) >> 1, pw = (w + 1) >> 1;
+  const int64_t b = blockIdx.x / (uint32_t)ph;
+  const int p0 = (int)(blockIdx.x - b * ph) * 2;
+  const uint32_t row_items = (uint32_t)pw * (uint32_t)c4;
+  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
+    const int pc = (int)(i / (uint32_t)c4);
+    const int cg = (int)(i - (uint32_t)pc * (uint32_t)c4);
+    const int q0 = pc * 2;
+    uint2 hv[16], lv[16];
+    bool ok[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ih = p0 - 1 + a, iw = q0 - 1 + c;
+        const bool v = ih >= 0 && ih < h && iw >= 0 && iw < w;
+        ok[a * 4 + c] = v;
+        const int64_t off = ((b * h + (v ? ih : 0)) * (int64_t)w + (v ? iw : 0)) * ldx + cg * 4;
+        hv[a * 4 + c] = __ldg(reinterpret_cast<const uint2*>(x_hi + off));
+        lv[a * 4 + c] = __ldg(reinterpret_cast<const uint2*>(x_lo + off));
+      }
+    // First-wins maxima with shared sub-results: per input row a, m12 = fw(col1, col2) feeds both R[a][0] = fw(col0, m12) and
+    // R[a][1] = fw(m12, col3); vertically v12 = fw(R[1], R[2]) feeds out(dp=0) = fw(R[0], v12) and out(dp=1) = fw(v12, R[3]).
+    // fw(x, y) keeps x unless y is strictly greater, i.e. the earlier element in TF scan order wins ties.  A state is
+    // (value, packed hi|lo word, position a*4+c); invalid taps carry -inf.
+    float best[4][4];
+    uint32_t bw[4][4], arg[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float rv[4][2]; uint32_t rw[4][2], rp[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float tv[4]; uint32_t tw[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t hwj = (j >> 1) ? hv[a * 4 + c].y : hv[a * 4 + c].x, lwj = (j >> 1) ? lv[a * 4 + c].y : lv[a * 4 + c].x;
+          tw[c] = __byte_perm(lwj, hwj, (j & 1) ? 0x7632 : 0x5410);
+          tv[c] = ok[a * 4 + c] ? __uint_as_float(tw[c] & 0xffff0000u) + __uint_as_float(tw[c] << 16) : -INFINITY;
+        }
+        const bool g12 = tv[2] > tv[1];
+        const float v12 = g12 ? tv[2] : tv[1]; const uint32_t w12 = g12 ? tw[2] : tw[1]; const uint32_t p12 = a * 4 + (g12 ? 2 : 1);
+        const bool g0 = v12 > tv[0];
+        rv[a][0] = g0 ? v12 : tv[0]; rw[a][0] = g0 ? w12 : tw[0]; rp[a][0] = g0 ? p12 : (uint32_t)(a * 4);
+        const bool g3 = tv[3] > v12;
+        rv[a][1] = g3 ? tv[3] : v12; rw[a][1] = g3 ? tw[3] : w12; rp[a][1] = g3 ? (uint32_t)(a * 4 + 3) : p12;
+      }
+#pragma unroll
+      for (int dq = 0; dq < 2; ++dq) {
+        const bool g12 = rv[2][dq] > rv[1][dq];
+        const float v12 = g12 ? rv[2][dq] : rv[1][dq]; const uint32_t w12 = g12 ? rw[2][dq] : rw[1][dq], p12 = g12 ? rp[2][dq] : rp[1][dq];
+        const bool g0 = v12 > rv[0][dq];
+        best[dq][j] = g0 ? v12 : rv[0][dq]; bw[dq][j] = g0 ? w12 : rw[0][dq];
+        const uint32_t pos0 = g0 ? p12 : rp[0][dq];
+        const bool g3 = rv[3][dq] > v12;
+        best[2 + dq][j] = g3 ? rv[3][dq] : v12; bw[2 + dq][j] = g3 ? rw[3][dq] : w12;
+        const uint32_t pos1 = g3 ? rp[3][dq] : p12;
+        // position (row a, col c) of the 4x4 patch -> tap index inside the output's own 3x3 window
+        arg[dq][j] = ((pos0 >> 2) - 0) * 3 + ((pos0 & 3) - dq);
+        arg[2 + dq][j] = ((pos1 >> 2) - 1) * 3 + ((pos1 & 3) - dq);
+      }
+    }
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp)
+#pragma unroll
+      for (int dq = 0; dq < 2; ++dq) {
+        const int p = p0 + dp, q = q0 + dq, o = dp * 2 + dq;
+        if (p >= h || q >= w) continue;
+        const int64_t oi = ((b * h + p) * (int64_t)w + q);
+        *reinterpret_cast<uint2*>(y_hi + oi * ldy + cg * 4) =
+            make_uint2((bw[o][0] >> 16) | (bw[o][1] & 0xffff0000u), (bw[o][2] >> 16) | (bw[o][3] & 0xffff0000u));
+        *reinterpret_cast<uint2*>(y_lo + oi * ldy + cg * 4) =
+            make_uint2((bw[o][0] & 0xffffu) | (bw[o][1] << 16), (bw[o][2] & 0xffffu) | (bw[o][3] << 16));
+        if (argmax)
+          *reinterpret_cast<uint32_t*>(argmax + (oi * c4 + cg) * 4) = arg[o][0] | (arg[o][1] << 8) | (arg[o][2] << 16) | (arg[o][3] << 24);
+      }
   }
 }
 
@@ -511,7 +600,10 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
   const int64_t total = batch * ho * wo * (c / 8);
   DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
-  if (k == 3)
+  if (k == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && ho == h && wo == w)
+    maxpool3s1_fwd_split_kernel<<<(unsigned)(batch * ((h + 1) / 2)), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 4),
+                                                                                            y_hi, y_lo, ldy, argmax);
+  else if (k == 3)
     maxpool_fwd_split_kernel<3><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
                                                                                 pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
   else
