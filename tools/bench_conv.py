@@ -66,7 +66,22 @@ for name, hw, cin, cout, ks in shapes:
     stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
     st = stats if (args.stats and name != "lstm step") else None
     t_new = time_it(lambda i: K.conv_bf16x3(xs[i], B, hw, hw, cin, ks, w, cout, K.View(cs[i]), stats=st))
-    line = "%-20s M=%8d K=%5d N=%4d  bf16x3 %8.3f ms %7.1f TFLOP/s (x3 issued: %7.1f)" % (name, M, kk, cout, t_new, fl / t_new / 1e9, 3 * fl / t_new / 1e9)
+    # floors: tensor pipe (3 passes, padded tile shapes, 2.25 PFLOP/s), HBM (A and C once, 6.4 TB/s), L2->SM operand traffic
+    # (every tile re-fetches its A and B chunks; ~9 TB/s observed ceiling)
+    tiles_n = -(-cout // 256)
+    while (M // 128) * tiles_n < 148 and (cout + tiles_n) // (tiles_n + 1) >= 32:
+        tiles_n += 1
+    bn = -(-(-(-cout // tiles_n)) // 32) * 32
+    tiles_n = -(-cout // bn)
+    cpt = -(-cin // 64)
+    iters = ks * ks * cpt
+    tiles = -(-M // 128) * tiles_n
+    nk = sum(-(-min(64, cin - c * 64) // 16) for c in range(cpt)) * ks * ks
+    t_mma = tiles * nk * 3 * (bn / 2.0) / 148 / 1.9e9 * 1e3
+    t_hbm = 4.0 * (M * cin + M * cout) / 6.4e12 * 1e3
+    t_l2 = tiles * iters * (32768 + 256 * bn) / 9e12 * 1e3
+    line = "%-20s M=%8d K=%5d N=%4d  bf16x3 %8.3f ms %7.1f TFLOP/s (x3 issued: %7.1f)  floors mma %.3f hbm %.3f l2 %.3f -> %3.0f%%" % (
+        name, M, kk, cout, t_new, fl / t_new / 1e9, 3 * fl / t_new / 1e9, t_mma, t_hbm, t_l2, 100 * max(t_mma, t_hbm, t_l2) / t_new)
     if args.old:
         xo = [torch.randn(M, cin, device=DEV) for _ in range(NBUF)]
         wo = torch.randn(cout, kk, device=DEV) * 0.05
