@@ -27,7 +27,7 @@ TOTAL_FLOP_TRAIN_PER_SAMPLE = 7.21e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE configs[2]/[3]: 256)")
@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the text tower on the main stream instead of a side stream")
     return ap.parse_args()
 
 
@@ -67,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -171,7 +172,8 @@ def run_ours(args):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 
     B = args.batch
-    eng = Engine(model=args.model, batch=B, precision=args.precision, device=local, seed=0, world_size=world, dropout="rng")
+    eng = Engine(model=args.model, batch=B, precision=args.precision, device=local, seed=0, world_size=world, dropout="rng",
+                 overlap_towers=not args.no_overlap)
     data = SyntheticPosts(num_samples=B * 4, seed=1234 + rank, with_images=args.model != "text", pool_batches=2)
     b0 = data.next_batch(B)
     b1 = data.next_batch(B)

@@ -99,6 +99,12 @@ int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, co
 /* same contract as ds_bn_relu_bwd_reduce; column-fixed row-streaming schedule used by the product path */
 int ds_bn_relu_bwd_reduce2(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n, const float* mean,
                            const float* rstd, const float* beta, double* sums, int64_t sums_ld, void* stream);
+/* ds_bn_finalize + ds_bn_apply_relu_split in one launch (train mode): batch mean / rstd from the fp64 sums stats[c],
+ * stats[stats_ld + c] over m rows; publishes mean_out / rstd_out and updates the moving averages (UPDATE_OPS) */
+int ds_bn_finalize_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, const double* stats, int64_t stats_ld,
+                                    float* moving_mean, float* moving_var, float momentum, float eps, const float* beta,
+                                    float* mean_out, float* rstd_out, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, int flags,
+                                    void* stream);
 int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
                                const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
@@ -196,9 +202,10 @@ int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const in
 int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const float* c_prev, const float* h_prev,
                       const int64_t* seq_len, int64_t t, int64_t batch, int64_t n, float forget_bias,
                       float* gates, float* c_out, float* h_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ldh, void* stream);
-/* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n] (+ optional split-bf16 copy); updates carries */
+/* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n] (+ optional split-bf16 copy); updates carries.
+ * dh_rec (optional) is consumed and left ZEROED, ready for the split-K recurrent contraction that accumulates into it. */
 int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len,
-                      int64_t t, int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc,
+                      int64_t t, int64_t batch, int64_t n, float* dh_rec, float* dh_carry, float* dc,
                       float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream);
 
 /* ---- head / loss / optimiser ------------------------------------------------------------ */

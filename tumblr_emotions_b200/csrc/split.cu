@@ -61,18 +61,50 @@ RowGrid row_grid(int64_t M, int64_t N, int ctas_per_sm, int min_rows = 0) {
 }
 
 // y = relu((z - mean) * rstd + beta) -> split planes
+// `stats` != NULL fuses ds_bn_finalize: mean / rstd come from the fp64 batch sums (stats[c], stats[stats_ld + c] over M rows),
+// and the first row-CTA publishes them (mean_out / rstd_out, for the backward pass) and updates the moving averages.
 __global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              float eps, const float* __restrict__ beta,
                                                              uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
-                                                             int64_t ldy, int flags, int rows_per_cta) {
+                                                             int64_t ldy, int flags, int rows_per_cta,
+                                                             const double* __restrict__ stats, int64_t stats_ld, float* mean_out,
+                                                             float* rstd_out, float* moving_mean, float* moving_var, float momentum) {
   const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (col >= N) return;
   const bool relu = !(flags & DS_BN_NO_RELU);
-  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + col));
-  float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + col));
+  float4 mu, rs;
+  if (stats) {
+    const double inv_m = 1.0 / (double)M;
+    float m4[4], r4[4], v4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double mean_d = stats[col + j] * inv_m;
+      double var_d = stats[stats_ld + col + j] * inv_m - mean_d * mean_d;
+      if (var_d < 0) var_d = 0;
+      m4[j] = (float)mean_d; v4[j] = (float)var_d; r4[j] = rsqrtf(v4[j] + eps);
+    }
+    mu = make_float4(m4[0], m4[1], m4[2], m4[3]);
+    rs = make_float4(r4[0], r4[1], r4[2], r4[3]);
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+      *reinterpret_cast<float4*>(mean_out + col) = mu;
+      *reinterpret_cast<float4*>(rstd_out + col) = rs;
+      if (moving_mean) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float mv_in = v4[j];
+          if ((flags & DS_BN_UNBIASED) && M > 1) mv_in = v4[j] * (float)((double)M / (double)(M - 1));
+          moving_mean[col + j] -= momentum * (moving_mean[col + j] - m4[j]);
+          moving_var[col + j] -= momentum * (moving_var[col + j] - mv_in);
+        }
+      }
+    }
+  } else {
+    mu = __ldg(reinterpret_cast<const float4*>(mean + col));
+    rs = __ldg(reinterpret_cast<const float4*>(rstd + col));
+    if (flags & DS_BN_USE_VAR) { rs.x = rsqrtf(rs.x + eps); rs.y = rsqrtf(rs.y + eps); rs.z = rsqrtf(rs.z + eps); rs.w = rsqrtf(rs.w + eps); }
+  }
   const float4 be = __ldg(reinterpret_cast<const float4*>(beta + col));
-  if (flags & DS_BN_USE_VAR) { rs.x = rsqrtf(rs.x + eps); rs.y = rsqrtf(rs.y + eps); rs.z = rsqrtf(rs.z + eps); rs.w = rsqrtf(rs.w + eps); }
   const int rl = blockDim.y;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   for (int64_t rb = r0 + threadIdx.y; rb < r1; rb += 4 * rl) {
@@ -555,7 +587,26 @@ int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, co
   DS_REQUIRE((((uintptr_t)y_hi | (uintptr_t)y_lo) & 7) == 0, "8-byte aligned planes");
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 16);
-  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, g.rows_per_cta);
+  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, g.rows_per_cta,
+                                                             nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_finalize_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, const double* stats, int64_t stats_ld,
+                                    float* moving_mean, float* moving_var, float momentum, float eps, const float* beta,
+                                    float* mean_out, float* rstd_out, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, int flags,
+                                    void* stream) {
+  DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
+  DS_REQUIRE(stats && mean_out && rstd_out, "needs stats, mean_out and rstd_out");
+  DS_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "moving_mean / moving_var go together");
+  DS_REQUIRE((((uintptr_t)mean_out | (uintptr_t)rstd_out | (uintptr_t)beta | (uintptr_t)z) & 15) == 0, "16-byte alignment");
+  DS_REQUIRE((((uintptr_t)y_hi | (uintptr_t)y_lo) & 7) == 0, "8-byte aligned planes");
+  if (m == 0 || n == 0) return 0;
+  const RowGrid g = row_grid(m, n, 16);
+  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, nullptr, nullptr, eps, beta, y_hi, y_lo, ldy, flags,
+                                                             g.rows_per_cta, stats, stats_ld, mean_out, rstd_out, moving_mean, moving_var,
+                                                             momentum);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
                                                              const float* __restrict__ c_cur,
                                                              const int64_t* __restrict__ seq_len, int64_t t, int64_t B, int n,
-                                                             const float* __restrict__ dh_rec, float* __restrict__ dh_carry,
+                                                             float* __restrict__ dh_rec, float* __restrict__ dh_carry,
                                                              float* __restrict__ dc, float* __restrict__ dz,
                                                              uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo, int64_t lddz) {
   const int n4 = n >> 2;
@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
     const bool live = t < seq_len[b];
     const int64_t sb = b * n + u, gbase = b * 4 * n + u;
     float4 dhr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dh_rec) dhr = *reinterpret_cast<const float4*>(dh_rec + sb);
+    if (dh_rec) {   // consumed here; left zeroed for the split-K recurrent GEMM of this step, which accumulates into it
+      dhr = *reinterpret_cast<const float4*>(dh_rec + sb);
+      *reinterpret_cast<float4*>(dh_rec + sb) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float4 dhc = *reinterpret_cast<const float4*>(dh_carry + sb);
     const float dh[4] = {dhr.x + dhc.x, dhr.y + dhc.y, dhr.z + dhc.z, dhr.w + dhc.w};
     if (!live) {   // state was carried: gradient passes through untouched, no gate gradient
@@ -176,7 +179,7 @@ int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const
 }
 
 int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len, int64_t t,
-                      int64_t batch, int64_t n, const float* dh_rec, float* dh_carry, float* dc, float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream) {
+                      int64_t batch, int64_t n, float* dh_rec, float* dh_carry, float* dc, float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream) {
   DS_REQUIRE(n % 4 == 0, "hidden size must be a multiple of 4");
   if (batch * n == 0) return 0;
   lstm_gates_bwd_kernel<<<blocks_for(batch * (n / 4)), 256, 0, ds::S(stream)>>>(gates, c_prev, c_cur, seq_len, t, batch, (int)n, dh_rec,

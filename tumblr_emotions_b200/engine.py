@@ -143,7 +143,12 @@ class ConvUnit:
                 ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
             if train:
                 ops.colstats(Zv, self.stats)
-        if train:
+        if train and self.split:      # finalize (mean / rstd / moving averages) fused into the apply launch of each segment
+            fl = ops.BN_UNBIASED if e.unbiased_moving_var else 0
+            for (c, n), out in zip(self.segs, self.outs):
+                ops.bn_finalize_apply_relu_split(Zv.slice(c, n), self.stats[c:], self.N, self.mov_mean[c:c + n], self.mov_var[c:c + n],
+                                                 1.0 - BN_DECAY, BN_EPS, self.beta[c:c + n], self.mean[c:c + n], self.rstd[c:c + n], out, fl)
+        elif train:
             ops.bn_finalize(self.stats, self.M, self.N, self.mov_mean, self.mov_var, 1.0 - BN_DECAY, BN_EPS, self.mean, self.rstd,
                             ops.BN_UNBIASED if e.unbiased_moving_var else 0)
             for (c, n), out in zip(self.segs, self.outs):
@@ -240,7 +245,8 @@ class Engine:
     def __init__(self, model: str = "joint", batch: int = 64, nb_emotions: int = 15, im_features: int = 256,
                  rnn_size: int = 1024, fc_size: int = 512, vocab: int = 400001, emb_dim: int = 50, post_size: int = 50,
                  precision: str = "bf16x3", device: int = 0, seed: int = 0, world_size: int = 1, dropout: str = "rng",
-                 unbiased_moving_var: bool = False, final_endpoint: str = "Mixed_5c", training: bool = True):
+                 unbiased_moving_var: bool = False, final_endpoint: str = "Mixed_5c", training: bool = True,
+                 overlap_towers: bool = True):
         if model not in ("joint", "image", "text"):
             raise ValueError("unknown model %r" % model)
         if precision not in ("bf16x3", "fp32"):
@@ -255,6 +261,7 @@ class Engine:
         self.rnn_size, self.fc_size, self.vocab, self.emb_dim, self.post_size = rnn_size, fc_size, vocab, emb_dim, post_size
         self.precision, self.world_size, self.dropout, self.unbiased_moving_var = precision, world_size, dropout, unbiased_moving_var
         self.training = training
+        self.overlap_towers, self._side = overlap_towers, None
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         ops.init(device)
@@ -603,14 +610,14 @@ class Engine:
         kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
         ops.copy2d(dlast, View(self.dh_carry))
         self.dc.zero_()
+        self.dh_rec.zero_()
         for t in reversed(range(T)):
             dzs = SView(self.DZs[t]) if self.split else None
             ops.lstm_gates_bwd(self.G[t], self.C[t], self.C[t + 1], self.seq_lens, t, B, n, self.dh_rec if t < T - 1 else None,
                                self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], dzs)
             if t > 0:
                 if self.split:      # K = 4n is long and M x N small: split-K keeps all SMs busy with 8x less operand traffic
-                    self.dh_rec.zero_()
-                    ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec), ksplit=8)
+                    ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec), ksplit=8)      # dh_rec was left zeroed by lstm_gates_bwd
                 else:
                     ops.gemm_nt(View(self.DZ[t * B:(t + 1) * B]), View(kern[e:]), View(self.dh_rec))
         dk = self.grad("Text/rnn/basic_lstm_cell/kernel")
@@ -650,8 +657,23 @@ class Engine:
         return View(self.logits, self.nb_emotions, 0)
 
     # -- forward ---------------------------------------------------------------------------------------------
+    # -- two-stream schedule: the text tower is independent of the image tower between the inputs and the head, and its
+    # kernels (one small GEMM + gate kernel per time step) leave most of the machine idle - run it on a side stream
+    def _fork(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side)
+
+    def _join(self):
+        torch.cuda.current_stream().wait_stream(self._side)
+
     def forward(self, train: bool = True):
         B = self.batch
+        overlap = self.model == "joint" and self.overlap_towers
+        if overlap:
+            with self._fork():
+                self.text_fwd(train)
         if self.has_image:
             for node in self.nodes:
                 node.fwd(train)
@@ -667,7 +689,9 @@ class Engine:
             bl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/biases")
             dst = View(self.concat, self.im_features, 0) if self.model == "joint" else self.logits_view()
             ops.gemm_nn(View(self.feat), View(wl), dst, bias=bl)
-        if self.has_text:
+        if overlap:
+            self._join()
+        elif self.has_text:
             self.text_fwd(train)
         if self.model == "joint":
             ops.copy2d(self.text_feat, View(self.concat, self.rnn_size, self.im_features))
@@ -707,7 +731,11 @@ class Engine:
             d_img, d_txt = None, View(self._dtxt)
         else:
             d_img, d_txt = dl, None
-        if self.has_text:
+        overlap = self.model == "joint" and self.overlap_towers
+        if overlap:
+            with self._fork():
+                self.text_bwd(d_txt)
+        elif self.has_text:
             self.text_bwd(d_txt)
         if self.has_image:
             wl = self.weight("InceptionV1/Logits/Conv2d_0c_1x1/weights").view(self.tower_c, self.tower_classes)
@@ -719,6 +747,8 @@ class Engine:
             ops.avgpool_dropout_bwd(View(self.dfeat), B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, self.d_tower_out)
             for node in reversed(self.nodes):
                 node.bwd()
+        if overlap:
+            self._join()
 
     # -- optimiser -------------------------------------------------------------------------------------------
     def set_lr(self, lr: float):

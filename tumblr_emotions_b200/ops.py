@@ -152,6 +152,12 @@ def bn_apply_relu_split(z: View, mean, rstd, eps, beta, y: SView, flags=0):
     lib().bn_apply_relu_split(z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), eps, _p(beta), y.ptr, y.lo_ptr, y.ld, flags, _stream())
 
 
+def bn_finalize_apply_relu_split(z: View, stats, stats_ld, moving_mean, moving_var, momentum, eps, beta, mean_out, rstd_out, y: SView,
+                                 flags=0):
+    lib().bn_finalize_apply_relu_split(z.ptr, z.ld, z.rows, z.cols, _p(stats), stats_ld, _p(moving_mean), _p(moving_var), momentum, eps,
+                                       _p(beta), _p(mean_out), _p(rstd_out), y.ptr, y.lo_ptr, y.ld, flags, _stream())
+
+
 def bn_relu_bwd_apply_split(dy: View, z: View, mean, rstd, beta, sums, sums_ld, dz: SView, dbeta):
     lib().bn_relu_bwd_apply_split(dy.ptr, dy.ld, z.ptr, z.ld, z.rows, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
                                   dz.ptr, dz.lo_ptr, dz.ld, _p(dbeta), _stream())
