@@ -80,13 +80,15 @@ int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t r
  * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w. */
 int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w,
                               int64_t cin, int ksize, uint16_t* o_hi, uint16_t* o_lo, int64_t ldo, void* stream);
-/* explicit im2col of the 7x7/2 stem conv (image_model/inception_v1.py:63; cin = 3, kw = 7) for output rows
- * [m_begin, m_begin + m_count): out[m - m_begin, r*kg + s*cin + c] = x[b, ho*stride - pad_t + r, wo*stride - pad_l + s, c] with
- * kg = roundup(kw*cin, 8) (each filter row is a zero-padded group of whole 16-byte stores); x is dense fp32 NHWC.  The rows then
- * feed ds_conv_bf16x3 as a 1x1 GEMM with K = kh*kg against weights repacked with fwd_rs = kg. */
-int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
-                              int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
-                              uint16_t* o_lo, int64_t ldo, void* stream);
+/* The 7x7/2 stem conv (image_model/inception_v1.py:63) in space-to-depth form.  ds_s2d_split: dense fp32 NHWC image [B,H,W,3] ->
+ * split planes S[b, P, Q+1, (dr*2+ds)*3 + c] = x[b, 2P+dr, 2Q+ds, c], shape [B, H/2, pitch_px, 16] each (channels 12..15 and the
+ * border pixels are zero).  ds_conv_s2d_rows: C[(b,p,q), n] = sum_{R<4, S<4, ch<16} S[b, p-1+R, q+S, ch] * W[n, R*64 + S*16 + ch],
+ * i.e. the 7x7/2 conv with TF-SAME padding (2,3) when W holds the 7x7 filter rearranged as W[n, R*64 + S*16 + (dr*2+ds)*3 + c] =
+ * w7[2R+dr, 2S+ds, c, n] (zero where 2R+dr or 2S+ds is 7).  One tile per output image row; rows = H/2, wout = W/2 <= 128. */
+int ds_s2d_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t pitch_px, uint16_t* s_hi, uint16_t* s_lo, void* stream);
+int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int64_t batch, int64_t rows, int64_t wout, int64_t pitch_px,
+                     const uint16_t* w_hi, const uint16_t* w_lo, int64_t ldb, int64_t n, float* c, int64_t ldc,
+                     double* stats, int flags, void* stream);
 /* HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld; filter-row stride fwd_rs, 0 = kw*cin) and
  * input-gradient operand [cin][kh'][kw'][cout] (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout: the fused sibling 1x1 convs of an inception block share
  * one operand whose K axis is the concatenation of their output channels) as split planes; either pair may be NULL */

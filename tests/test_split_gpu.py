@@ -235,3 +235,32 @@ def test_avgpool_split(K):
     K.avgpool_dropout_fwd_split(X, b, hw, c, mask.to(DEV), 1.25, K.View(out))
     ref = X.torch().cpu().view(b, hw, c).double().mean(1) * mask.double() * 1.25
     close(out, ref, 1e-6, "avgpool split")
+
+
+@pytest.mark.parametrize("b,hw,n", [(2, 32, 64), (3, 64, 64), (1, 224, 64), (2, 16, 24)])
+def test_stem_conv_space_to_depth_matches_oracle(K, b, hw, n):
+    """7x7 / stride 2 / TF-SAME (2,3) conv via ds_s2d_split + ds_conv_s2d_rows against the oracle's conv2d"""
+    g = gen(13)
+    x = torch.rand(b, hw, hw, 3, generator=g) * 2 - 1
+    w = torch.randn(7, 7, 3, n, generator=g) * 0.1
+    ref = O.conv2d(x.double(), w.double(), 2).reshape(-1, n)
+    ho = hw // 2
+    pitch = ho + 3
+    s_hi = torch.zeros(b, ho, pitch, 16, dtype=torch.bfloat16, device=DEV)
+    s_lo = torch.zeros_like(s_hi)
+    K.s2d_split(x.to(DEV), pitch, s_hi, s_lo)
+    s = (s_hi.float() + s_lo.float()).cpu()
+    assert float(s[:, :, 0].abs().max()) == 0 and float(s[:, :, ho + 1:].abs().max()) == 0 and float(s[..., 12:].abs().max()) == 0
+    xs = x.view(b, ho, 2, ho, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(b, ho, ho, 12)
+    assert float((s[:, :, 1:ho + 1, :12] - xs).abs().max()) <= 2.0 ** -16
+    w8 = torch.zeros(8, 8, 3, n)
+    w8[:7, :7] = w
+    w4 = torch.zeros(n, 4, 4, 16)
+    w4[..., :12] = w8.view(4, 2, 4, 2, 3, n).permute(5, 0, 2, 1, 3, 4).reshape(n, 4, 4, 12)
+    W = to_split(K, w4.view(n, 256))
+    c = torch.full((b * ho * ho, n), 3.0, device=DEV)
+    stats = torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+    K.conv_s2d_rows(s_hi, s_lo, b, ho, ho, pitch, W, n, K.View(c), stats=stats)
+    close(c, ref, 1e-4, "s2d stem conv")
+    close(stats[:n], ref.sum(0), 1e-4, "stats sum")
+    close(stats[n:], (ref * ref).sum(0), 1e-4, "stats sumsq")

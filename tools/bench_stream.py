@@ -85,9 +85,4 @@ for name, px, n in bns:
     report("bwd apply  " + name, ms, 12 * M * n)
     del zs, dys, ys
 
-if want("im2col"):
-    imgs = torch.randn(16, 224, 224, 3, device=DEV)
-    col = K.SView(K.new_split((16 * 112 * 112,), 168, DEV))
-    ms = time_it(lambda i: K.im2col_small_cin_split(imgs, 16, 224, 224, 3, 7, 7, 2, 2, 2, 112, 112, 0, 16 * 112 * 112, col))
-    report("im2col stem, 16 images", ms, 16 * 112 * 112 * 168 * 4 + imgs.numel() * 4)
 print({k: "%.1f us" % (v * 1e3) for k, v in tot.items()})

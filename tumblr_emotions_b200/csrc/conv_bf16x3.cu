@@ -57,13 +57,16 @@ struct Params {
   int h, w, pad;
   int stages;
   int nstg;          // epilogue staging tiles (1 or 2)
+  int row_mode;      // 1: space-to-depth stem - one tile per output image row, A = overlapping 4-pixel windows (ds_conv_s2d_rows)
+  int tile_rows;     // valid rows per tile: 128, or the output width in row mode
+  int rows_per_img;  // row mode: output rows per image
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t& m0, int& n0, int& it0, int& it1) {
   const int z = (int)(t % p.ksplit);
   const int64_t q = t / p.ksplit;
   n0 = (int)(q % p.tiles_n) * p.bn;
-  m0 = (q / p.tiles_n) * BM;
+  m0 = (q / p.tiles_n) * p.tile_rows;
   it0 = z * p.ipz;
   it1 = min(p.iters, it0 + p.ipz);
 }
@@ -132,11 +135,18 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t ph = (g / p.stages) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, stage_bytes);
+          mbar_expect_tx(fb, p.row_mode ? 2u * (uint32_t)p.tile_rows * 128u + 2u * b_tile_bytes : stage_bytes);
           const int tap = it / p.cpt;
           const int c0 = (it - tap * p.cpt) * KC;
           const uint32_t sa = base + s * stage_bytes;
-          if (p.ksize == 1) {
+          if (p.row_mode) {
+            // output row (img, prow): filter-row group `it` reads space-to-depth row prow - 1 + it (zero outside the image);
+            // the box is {64 = 4 pixels x 16 channels, W_out windows one pixel apart}
+            const int tile = (int)(m0 / p.tile_rows);
+            const int bimg = tile / p.rows_per_img, prow = tile - bimg * p.rows_per_img;
+            tma_load_4d(&tmAh, fb, sa, 0, 0, prow - 1 + it, bimg);
+            tma_load_4d(&tmAl, fb, sa + A_TILE_BYTES, 0, 0, prow - 1 + it, bimg);
+          } else if (p.ksize == 1) {
             tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
             tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
           } else {
@@ -242,7 +252,8 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             const uint32_t row = (uint32_t)(quarter * 32 + rr);
-            const float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
+            float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
+            if ((int)row >= p.tile_rows) x = 0.f;          // row mode: rows past the image row hold garbage
             a1 += x;
             a2 = fmaf(x, x, a2);
           }
@@ -321,6 +332,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   DS_REQUIRE(p.bn % 32 == 0 && p.bn >= 32 && p.bn <= 256, "column tile must be a multiple of 32 in [32, 256]");
   p.tiles = ds::cdiv(M, BM) * p.tiles_n * p.ksplit;
   p.h = (int)h; p.w = (int)w; p.pad = (ksize - 1) / 2;
+  p.row_mode = 0; p.tile_rows = BM; p.rows_per_img = 0;
   const int64_t ktot = (int64_t)ksize * ksize * cin;
 
   CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
@@ -360,6 +372,66 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
+  conv_bf16x3_kernel<<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Space-to-depth formulation of the 7x7 / stride-2 stem conv (image_model/inception_v1.py:63): with 2x2 pixel blocks folded into
+// channels (12 -> 16) the conv becomes a 4x4 / stride-1 conv, and the 4 horizontal taps of one filter row are 64 CONTIGUOUS
+// elements of the NHWC space-to-depth image - a K chunk is one plain 4-D tiled TMA box over overlapping windows, no im2col
+// blow-up.  One tile = one output image row (tile_rows = W_out <= 128); 4 K chunks (filter-row groups) per tile.
+extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int64_t batch, int64_t rows, int64_t wout, int64_t pitch_px,
+                                const uint16_t* w_hi, const uint16_t* w_lo, int64_t ldb, int64_t n, float* c, int64_t ldc,
+                                double* stats, int flags, void* stream) {
+  DS_REQUIRE(ds::g_encode_tiled, "ds_init() has not been called");
+  DS_REQUIRE(wout <= BM && wout % 8 == 0 && pitch_px >= wout + 3, "output width must be <= 128 and the pixel pitch >= W_out + 3");
+  DS_REQUIRE(n % 4 == 0 && n <= 256 && ldb % 8 == 0 && ldc % 4 == 0, "alignment (see deepsent.h)");
+  DS_REQUIRE((((uintptr_t)s_hi | (uintptr_t)s_lo | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)c) & 15) == 0, "16-byte aligned bases");
+  DS_REQUIRE(!(flags & ~DS_EPI_STATS), "only the stats epilogue is supported");
+  DS_REQUIRE(!(flags & DS_EPI_STATS) || stats != nullptr, "DS_EPI_STATS needs a stats buffer");
+  const int64_t M = batch * rows * wout;
+  if (M == 0 || n == 0) return 0;
+  const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
+  Params p;
+  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = nullptr; p.bias = nullptr; p.stats = stats; p.flags = flags;
+  p.bn = (int)((n + 31) / 32 * 32);
+  p.tiles_n = 1; p.ksplit = 1;
+  p.ksize = 1; p.cin = KC; p.cpt = 1; p.iters = 4; p.ipz = 4;
+  p.tiles = batch * rows;
+  p.h = 0; p.w = 0; p.pad = 0;
+  p.row_mode = 1; p.tile_rows = (int)wout; p.rows_per_img = (int)rows;
+
+  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
+  int r = 0;
+  for (int plane = 0; plane < 2 && !r; ++plane) {
+    // dims {64 window elements, W_out windows (one 16-channel pixel apart), rows, images}
+    cuuint64_t dims[4] = {64, (cuuint64_t)wout, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {16 * 2, (cuuint64_t)pitch_px * 16 * 2, (cuuint64_t)rows * pitch_px * 16 * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)wout, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult cr = ds::g_encode_tiled(plane ? &tmAl : &tmAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                     const_cast<uint16_t*>(plane ? s_lo : s_hi), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = cr == CUDA_SUCCESS ? 0 : (int)cr;
+  }
+  if (r) return ds::fail("cuTensorMapEncode(space-to-depth A) failed: CUresult %d", r);
+  r = ds::make_tmap_2d_bf16(&tmBh, w_hi, (uint64_t)n, 256, (uint64_t)ldb, KC, (uint32_t)p.bn);
+  if (!r) r = ds::make_tmap_2d_bf16(&tmBl, w_lo, (uint64_t)n, 256, (uint64_t)ldb, KC, (uint32_t)p.bn);
+  if (r) return ds::fail("cuTensorMapEncode(B) failed: CUresult %d", r);
+  r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, (uint32_t)wout, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d", r);
+
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
+  const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);
+  p.nstg = 2;
+  int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + fixed;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int64_t grid = std::min<int64_t>(p.tiles, sms);
   conv_bf16x3_kernel<<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;

@@ -455,45 +455,40 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
   }
 }
 
-// Explicit im2col of a small-Cin strided convolution (the 7x7/2 stem, image_model/inception_v1.py:63) into the split-bf16
-// GEMM operand.  K layout: kh groups of kg = roundup(kw*cin, 8) entries, group r = [x[ih0 + r, iw0 .. iw0 + kw - 1, 0..cin-1] | 0 pad]
-// - one filter row is a contiguous run of kw*cin floats in the NHWC image, and a group is whole 16-byte stores.
-// One thread per (output pixel, filter row).
-template <int CIN, int KW>
-__global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restrict__ x, int64_t m_begin, int64_t m_count, int h, int w,
-                                                          int kh, int stride, int pad_t, int pad_l, int ho, int wo,
-                                                          uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int64_t ldo) {
-  constexpr int RUN = KW * CIN, KG = (RUN + 7) / 8 * 8;
-  const int64_t total = m_count * kh;
+// Space-to-depth of the fp32 NHWC image for the stem (ds_conv_s2d_rows): S[b, P, Q + 1, (dr*2 + ds)*3 + c] = x[b, 2P + dr, 2Q + ds, c]
+// as split-bf16 planes [B, H/2, pitch_px, 16]; channels 12..15 and the border pixels 0, W/2 + 1 .. pitch_px - 1 are zero.
+// One thread per output pixel: 16 channels = two 16-byte stores per plane.
+__global__ void __launch_bounds__(256) s2d_split_kernel(const float* __restrict__ x, int64_t B, int h, int w, int pitch_px,
+                                                        uint16_t* __restrict__ s_hi, uint16_t* __restrict__ s_lo) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const int64_t total = B * h2 * (int64_t)pitch_px;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i % kh);
-    const int64_t ml = i / kh;
-    const int64_t m = m_begin + ml;
-    const int q = (int)(m % wo);
-    const int64_t t2 = m / wo;
-    const int p = (int)(t2 % ho);
-    const int64_t b = t2 / ho;
-    const int ih = p * stride - pad_t + r, iw0 = q * stride - pad_l;
-    const bool row_ok = ih >= 0 && ih < h;
-    const float* src = x + ((b * h + (row_ok ? ih : 0)) * (int64_t)w + iw0) * CIN;
-    uint32_t hh[KG], ll[KG];
+    const int qp = (int)(i % pitch_px);
+    const int64_t t = i / pitch_px;
+    const int P = (int)(t % h2);
+    const int64_t b = t / h2;
+    uint32_t hh[16], ll[16];
 #pragma unroll
-    for (int j = 0; j < KG; ++j) {
-      float v = 0.f;
-      if (j < RUN) {
-        const int iw = iw0 + j / CIN;
-        if (row_ok && iw >= 0 && iw < w) v = __ldg(src + j);
+    for (int j = 0; j < 16; ++j) { hh[j] = 0; ll[j] = 0; }
+    const int Q = qp - 1;
+    if (Q >= 0 && Q < w2) {
+#pragma unroll
+      for (int dr = 0; dr < 2; ++dr) {
+        // the two horizontally adjacent pixels of row 2P + dr are 6 contiguous floats
+        const float* src = x + ((b * h + 2 * P + dr) * (int64_t)w + 2 * Q) * 3;
+        const float2 v0 = __ldg(reinterpret_cast<const float2*>(src)), v1 = __ldg(reinterpret_cast<const float2*>(src + 2)),
+                     v2 = __ldg(reinterpret_cast<const float2*>(src + 4));
+        const float v[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ds::split_bf16(v[k], hh[dr * 6 + k], ll[dr * 6 + k]);
       }
-      ds::split_bf16(v, hh[j], ll[j]);
     }
-    const int64_t o = ml * ldo + r * KG;
-#pragma unroll
-    for (int j = 0; j < KG; j += 8) {
-      *reinterpret_cast<uint4*>(o_hi + o + j) =
-          make_uint4(hh[j] | (hh[j + 1] << 16), hh[j + 2] | (hh[j + 3] << 16), hh[j + 4] | (hh[j + 5] << 16), hh[j + 6] | (hh[j + 7] << 16));
-      *reinterpret_cast<uint4*>(o_lo + o + j) =
-          make_uint4(ll[j] | (ll[j + 1] << 16), ll[j + 2] | (ll[j + 3] << 16), ll[j + 4] | (ll[j + 5] << 16), ll[j + 6] | (ll[j + 7] << 16));
-    }
+    uint4* dh = reinterpret_cast<uint4*>(s_hi + i * 16);
+    uint4* dl = reinterpret_cast<uint4*>(s_lo + i * 16);
+    dh[0] = make_uint4(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16), hh[4] | (hh[5] << 16), hh[6] | (hh[7] << 16));
+    dh[1] = make_uint4(hh[8] | (hh[9] << 16), hh[10] | (hh[11] << 16), 0, 0);
+    dl[0] = make_uint4(ll[0] | (ll[1] << 16), ll[2] | (ll[3] << 16), ll[4] | (ll[5] << 16), ll[6] | (ll[7] << 16));
+    dl[1] = make_uint4(ll[8] | (ll[9] << 16), ll[10] | (ll[11] << 16), 0, 0);
   }
 }
 
@@ -687,17 +682,12 @@ int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_
   return 0;
 }
 
-int ds_im2col_small_cin_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t cin, int kh, int kw, int stride,
-                              int pad_t, int pad_l, int64_t ho, int64_t wo, int64_t m_begin, int64_t m_count, uint16_t* o_hi,
-                              uint16_t* o_lo, int64_t ldo, void* stream) {
-  DS_REQUIRE(cin == 3 && kw == 7, "ds_im2col_small_cin_split is specialised for the 7x7x3 stem (image_model/inception_v1.py:63)");
-  const int kg = (int)((kw * cin + 7) / 8 * 8);
-  DS_REQUIRE(ldo % 8 == 0 && ldo >= (int64_t)kh * kg, "output row stride must be a multiple of 8 and cover kh * roundup(kw*cin, 8)");
-  DS_REQUIRE((((uintptr_t)o_hi | (uintptr_t)o_lo) & 15) == 0, "16-byte aligned planes");
-  DS_REQUIRE(m_begin >= 0 && m_begin + m_count <= batch * ho * wo, "row range outside the output");
-  if (m_count == 0) return 0;
-  im2col_rows_kernel<3, 7><<<ew_blocks(m_count * kh), 256, 0, ds::S(stream)>>>(x, m_begin, m_count, (int)h, (int)w, kh, stride, pad_t, pad_l,
-                                                                             (int)ho, (int)wo, o_hi, o_lo, ldo);
+int ds_s2d_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t pitch_px, uint16_t* s_hi, uint16_t* s_lo, void* stream) {
+  DS_REQUIRE(h % 2 == 0 && w % 2 == 0 && pitch_px >= w / 2 + 3, "even image size, pixel pitch >= W/2 + 3");
+  DS_REQUIRE((((uintptr_t)s_hi | (uintptr_t)s_lo) & 15) == 0 && (((uintptr_t)x) & 7) == 0, "aligned buffers");
+  const int64_t total = batch * (h / 2) * pitch_px;
+  if (total == 0) return 0;
+  s2d_split_kernel<<<ew_blocks(total), 256, 0, ds::S(stream)>>>(x, batch, (int)h, (int)w, (int)pitch_px, s_hi, s_lo);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -77,12 +77,16 @@ class ConvUnit:
             self.w_fwd = SView(eng.new_split((self.N,), kk * cin))           # [N][r][s][cin]
             self.w_dgrad = SView(eng.new_split((cin,), kk * self.N))         # [cin][r'][s'][N]
         elif self.stem_tc:
-            self.kg = (k * cin + 7) // 8 * 8                                 # one filter row = a zero-padded group of 16-byte stores
-            self.k8 = k * self.kg
-            self.w_fwd = SView(eng.new_split((self.N,), self.k8))            # [N][r][(s,c) zero-padded to kg]
+            # space-to-depth form: 2x2 pixel blocks folded into channels turn the 7x7/2 conv into a 4x4/1 conv whose filter rows are
+            # contiguous 64-element windows of the NHWC image (ds_conv_s2d_rows)
+            assert k == 7 and stride == 2 and cin == 3 and h_in % 2 == 0
+            self.s2d_pitch = h_in // 2 + 3
+            self.s2d_hi = torch.zeros(eng.batch, h_in // 2, self.s2d_pitch, 16, dtype=torch.bfloat16, device=eng.device)
+            self.s2d_lo = torch.zeros_like(self.s2d_hi)
+            eng._bytes += 2 * self.s2d_hi.numel() * 2
+            self.w_fwd = SView(eng.new_split((self.N,), 256))                # [N][R][S][(dr,ds,c) padded to 16]
+            self._w4 = eng.new(self.N, 256)
             self.w_dgrad = None
-            self.chunk_imgs = min(eng.batch, 16)                             # 16 images x 12544 pixels x 608 B = 122 MB ~ L2
-            self.col = SView(eng.new_split((self.chunk_imgs * self.h_out * self.h_out,), self.k8))
         else:
             self.w_fwd = None
             self.w_dgrad = eng.new(cin, kk * self.N)                          # fp32 [cin][r'][s'][N]
@@ -102,7 +106,12 @@ class ConvUnit:
             if self.tc:
                 ops.repack_conv_weights_split(w, fwd=self.w_fwd.rows_slice(c, n), dgrad=self.w_dgrad.slice(c, n), dgrad_tap=self.N)
             elif self.stem_tc:
-                ops.repack_conv_weights_split(w, fwd=self.w_fwd, fwd_rs=self.kg)
+                w8 = torch.zeros(8, 8, 3, self.N, device=w.device)
+                w8[:7, :7] = w                                               # tap r = 2R + dr, s = 2S + ds; r, s = 7 are zero
+                w4 = w8.view(4, 2, 4, 2, 3, self.N).permute(5, 0, 2, 1, 3, 4).reshape(self.N, 4, 4, 12)
+                self._w4.zero_()
+                self._w4.view(self.N, 4, 4, 16)[..., :12] = w4
+                ops.split_bf16(View(self._w4), self.w_fwd)
             else:
                 ops.repack_conv_weights(w, fwd=None, dgrad=View(self.w_dgrad.view(self.cin * kk, self.N), n, c), dgrad_ld=self.N,
                                         round_tf32=False)
@@ -128,13 +137,9 @@ class ConvUnit:
         if self.tc:
             ops.conv_bf16x3(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.N, Zv, stats=self.stats if train else None)
         elif self.stem_tc:
-            px = self.h_out * self.h_out
-            for b0 in range(0, B, self.chunk_imgs):
-                nb = min(self.chunk_imgs, B - b0)
-                ops.im2col_small_cin_split(self.x.base, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out,
-                                           self.h_out, b0 * px, nb * px, self.col)
-                ops.conv_bf16x3(self.col.rows_slice(0, nb * px), nb * px, 1, 1, self.k8, 1, self.w_fwd, self.N,
-                                View(self.Z[b0 * px:(b0 + nb) * px]), stats=self.stats if train else None)
+            ops.s2d_split(self.x.base, self.s2d_pitch, self.s2d_hi, self.s2d_lo)
+            ops.conv_s2d_rows(self.s2d_hi, self.s2d_lo, B, self.h_out, self.h_out, self.s2d_pitch, self.w_fwd, self.N, Zv,
+                              stats=self.stats if train else None)
         else:
             if len(self.scopes) == 1:
                 ops.conv_simt(self.x, B, h, h, self.cin, self.k, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,

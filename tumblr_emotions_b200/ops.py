@@ -127,9 +127,14 @@ def im2col_transpose_split(x: SView, batch, h, w, cin, ksize, out: SView):
     lib().im2col_transpose_split(x.ptr, x.lo_ptr, x.ld, batch, h, w, cin, ksize, out.ptr, out.lo_ptr, out.ld, _stream())
 
 
-def im2col_small_cin_split(x: torch.Tensor, batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, m_begin, m_count, out: SView):
-    lib().im2col_small_cin_split(x.data_ptr(), batch, h, w, cin, kh, kw, stride, pad_t, pad_l, ho, wo, m_begin, m_count, out.ptr,
-                                 out.lo_ptr, out.ld, _stream())
+def s2d_split(x: torch.Tensor, pitch_px: int, s_hi: torch.Tensor, s_lo: torch.Tensor):
+    b, h, w, _ = x.shape
+    lib().s2d_split(x.data_ptr(), b, h, w, pitch_px, s_hi.data_ptr(), s_lo.data_ptr(), _stream())
+
+
+def conv_s2d_rows(s_hi: torch.Tensor, s_lo: torch.Tensor, batch, rows, wout, pitch_px, w: SView, n, c: View, stats=None):
+    lib().conv_s2d_rows(s_hi.data_ptr(), s_lo.data_ptr(), batch, rows, wout, pitch_px, w.ptr, w.lo_ptr, w.ld, n, c.ptr, c.ld, _p(stats),
+                        EPI_STATS if stats is not None else 0, _stream())
 
 
 def masked_colsum_split(dy: View, y: SView, sums):
