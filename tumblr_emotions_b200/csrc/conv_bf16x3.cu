@@ -71,6 +71,7 @@ __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t&
   it1 = min(p.iters, it0 + p.ipz);
 }
 
+template <bool ROW_MODE>      // compile-time copy of p.row_mode: the generic path carries none of the stem's extra work
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -135,11 +136,11 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t ph = (g / p.stages) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, p.row_mode ? 2u * (uint32_t)p.tile_rows * 128u + 2u * b_tile_bytes : stage_bytes);
+          mbar_expect_tx(fb, ROW_MODE ? 2u * (uint32_t)p.tile_rows * 128u + 2u * b_tile_bytes : stage_bytes);
           const int tap = it / p.cpt;
           const int c0 = (it - tap * p.cpt) * KC;
           const uint32_t sa = base + s * stage_bytes;
-          if (p.row_mode) {
+          if (ROW_MODE) {
             // output row (img, prow): filter-row group `it` reads space-to-depth row prow - 1 + it (zero outside the image);
             // the box is {64 = 4 pixels x 16 channels, W_out windows one pixel apart}
             const int tile = (int)(m0 / p.tile_rows);
@@ -253,7 +254,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           for (int rr = 0; rr < 32; ++rr) {
             const uint32_t row = (uint32_t)(quarter * 32 + rr);
             float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
-            if ((int)row >= p.tile_rows) x = 0.f;          // row mode: rows past the image row hold garbage
+            if (ROW_MODE && (int)row >= p.tile_rows) x = 0.f;          // row mode: rows past the image row hold garbage
             a1 += x;
             a2 = fmaf(x, x, a2);
           }
@@ -364,7 +365,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   if (smem < 120 * 1024) smem = 120 * 1024;     // one CTA per SM: each CTA owns all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
-    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   // a CTA must keep the same column tile for all its tiles (register-resident batch-norm partial sums): with tiles
@@ -372,7 +373,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
-  conv_bf16x3_kernel<<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -430,9 +431,9 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t grid = std::min<int64_t>(p.tiles, sms);
-  conv_bf16x3_kernel<<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<true><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }
