@@ -119,7 +119,9 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      uint32_t g = 0;      // global K-iteration counter (ring position)
+      // ring position (slot s, phase ph) and the (tap, channel chunk) of an iteration advance incrementally: the loop
+      // that feeds the tensor cores carries no integer division
+      int s = 0; uint32_t ph = 0;
       for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
@@ -131,14 +133,13 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           hp = rem / p.w;
           wq = rem - hp * p.w;
         }
-        for (int it = it0; it < it1; ++it, ++g) {
-          const int s = g % p.stages;
-          const uint32_t ph = (g / p.stages) & 1u;
+        int tap = it0 / p.cpt, cc = it0 - tap * p.cpt;            // channel chunk within the tap
+        int r = tap / p.ksize, sx = tap - r * p.ksize;
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t fb = full0 + 8 * s;
           mbar_expect_tx(fb, ROW_MODE ? 2u * (uint32_t)p.tile_rows * 128u + 2u * b_tile_bytes : stage_bytes);
-          const int tap = it / p.cpt;
-          const int c0 = (it - tap * p.cpt) * KC;
+          const int c0 = cc * KC;
           const uint32_t sa = base + s * stage_bytes;
           if (ROW_MODE) {
             // output row (img, prow): filter-row group `it` reads space-to-depth row prow - 1 + it (zero outside the image);
@@ -151,13 +152,14 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
             tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
           } else {
-            const int r = tap / p.ksize, sx = tap - r * p.ksize;
             tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
             tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
           }
           const int kb = tap * p.cin + c0;
           tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
           tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          if (++cc == p.cpt) { cc = 0; ++tap; if (++sx == p.ksize) { sx = 0; ++r; } }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -165,7 +167,9 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.bn);
-      uint32_t g = 0, acc_it = 0;
+      uint32_t acc_it = 0;
+      int s = 0; uint32_t ph = 0;
+      const int nk_full = KC >> 4, nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;      // 16-channel steps per chunk
       for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
@@ -173,13 +177,12 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         mbar_wait(tempty0 + 8 * buf, aph ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * ACC_COLS;
-        for (int it = it0; it < it1; ++it, ++g) {
-          const int s = g % p.stages;
-          const uint32_t ph = (g / p.stages) & 1u;
+        int cc = it0 % p.cpt;
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const int c0 = (it % p.cpt) * KC;
-          const int nk = (min(KC, p.cin - c0) + 15) >> 4;
+          const int nk = (cc == p.cpt - 1) ? nk_last : nk_full;
+          if (++cc == p.cpt) cc = 0;
           const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES, bh = al + A_TILE_BYTES, bl = bh + b_tile_bytes;
           for (int k = 0; k < nk; ++k) {
             const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
@@ -189,6 +192,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             mma_f16(acc, dah, dbh, idesc, 1u);
           }
           mma_commit(empty0 + 8 * s);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         mma_commit(tfull0 + 8 * buf);
       }
