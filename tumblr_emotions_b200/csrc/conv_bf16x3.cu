@@ -80,12 +80,15 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-  const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+  const uint32_t stage_bytes = ROW_MODE ? 2u * A_TILE_BYTES : 2u * A_TILE_BYTES + 2u * b_tile_bytes;   // row mode: B is resident
   const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;   // epilogue staging tiles (1024-aligned, 16 KB each)
-  const uint32_t bars = stg0 + (uint32_t)p.nstg * STG_BYTES;
+  // row mode keeps the whole (small) weight operand resident: 4 K chunks x {hi, lo} x bn rows, fetched once per CTA
+  const uint32_t bres = stg0 + (uint32_t)p.nstg * STG_BYTES;
+  const uint32_t bars = bres + (ROW_MODE ? 8u * b_tile_bytes : 0u);
   // full[s] at bars + 8*s, empty[s] at bars + 64 + 8*s, tmem_full[b] at bars + 128 + 8*b, tmem_empty[b] at bars + 144 + 8*b,
   // tmem base pointer at bars + 160
   const uint32_t full0 = bars, empty0 = bars + 64, tfull0 = bars + 128, tempty0 = bars + 144, tmem_slot = bars + 160;
+  const uint32_t bres_bar = bars + 176;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   // cross-warp reduction of the batch-norm partial sums of this CTA's column tile: [2][bn] fp64
   double* sred = reinterpret_cast<double*>(smem_raw + (bars + 256 - raw));
@@ -101,6 +104,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
+    mbar_init(bres_bar, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
       mbar_init(tempty0 + 8 * b, 4);      // one arrive per epilogue warp
@@ -122,6 +126,13 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       // ring position (slot s, phase ph) and the (tap, channel chunk) of an iteration advance incrementally: the loop
       // that feeds the tensor cores carries no integer division
       int s = 0; uint32_t ph = 0;
+      if (ROW_MODE) {
+        mbar_expect_tx(bres_bar, 8u * b_tile_bytes);
+        for (int c = 0; c < 4; ++c) {
+          tma_load_2d(&tmBh, bres_bar, bres + (2 * c) * b_tile_bytes, c * KC, 0);
+          tma_load_2d(&tmBl, bres_bar, bres + (2 * c + 1) * b_tile_bytes, c * KC, 0);
+        }
+      }
       for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
@@ -138,7 +149,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         for (int it = it0; it < it1; ++it) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, ROW_MODE ? 2u * (uint32_t)p.tile_rows * 128u + 2u * b_tile_bytes : stage_bytes);
+          mbar_expect_tx(fb, ROW_MODE ? 2u * (uint32_t)p.tile_rows * 128u : stage_bytes);
           const int c0 = cc * KC;
           const uint32_t sa = base + s * stage_bytes;
           if (ROW_MODE) {
@@ -155,9 +166,11 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
             tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
           }
-          const int kb = tap * p.cin + c0;
-          tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
-          tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          if (!ROW_MODE) {
+            const int kb = tap * p.cin + c0;
+            tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
+            tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          }
           if (++cc == p.cpt) { cc = 0; ++tap; if (++sx == p.ksize) { sx = 0; ++r; } }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -170,6 +183,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       uint32_t acc_it = 0;
       int s = 0; uint32_t ph = 0;
       const int nk_full = KC >> 4, nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;      // 16-channel steps per chunk
+      if (ROW_MODE) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
@@ -183,7 +197,8 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           tc_fence_after();
           const int nk = (cc == p.cpt - 1) ? nk_last : nk_full;
           if (++cc == p.cpt) cc = 0;
-          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES, bh = al + A_TILE_BYTES, bl = bh + b_tile_bytes;
+          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES;
+          const uint32_t bh = ROW_MODE ? bres + (uint32_t)(2 * it) * b_tile_bytes : al + A_TILE_BYTES, bl = bh + b_tile_bytes;
           for (int k = 0; k < nk; ++k) {
             const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
@@ -427,13 +442,15 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, (uint32_t)wout, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d", r);
 
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
+  const int stage_bytes = 2 * A_TILE_BYTES;                       // ring slots hold only the activation planes
   const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);
+  const int resident_b = 8 * p.bn * 128;
   p.nstg = 2;
-  int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES) / stage_bytes;
+  int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES - resident_b) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  DS_REQUIRE(stages >= 2, "shared-memory budget exceeded");
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + fixed;
+  size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + resident_b + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;
   DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t grid = std::min<int64_t>(p.tiles, sms);
