@@ -204,3 +204,46 @@ def test_against_committed_golden_vectors(model):
     for name, ref in g["grad_l2"].items():
         got = float(eng.tensor(name, "grads").double().norm())
         assert abs(got - ref) <= 0.05 * ref + 1e-12, (name, got, ref)
+
+
+@pytest.mark.parametrize("lens", ["all_one", "all_max", "ragged"])
+def test_text_tower_sequence_length_edges(lens):
+    """dynamic_rnn(sequence_length=...) edge cases: length 1 (state frozen after the first step), the maximum 50 (no masking)
+    and ragged batches; the feature is h[len-1] (im_text_rnn_model.py:89-92)."""
+    from tumblr_emotions_b200.engine import Engine
+    batch = 6
+    eng = Engine(model="text", batch=batch, precision="bf16x3", vocab=VOCAB, dropout="none")
+    p = O.init_params(3, "text", vocab=VOCAB)
+    eng.load_state_dict(p)
+    bd = O.synthetic_batch(batch, seed=77, vocab=VOCAB, with_images=False)
+    if lens == "all_one":
+        bd["seq_lens"] = torch.ones(batch, dtype=torch.int64)
+    elif lens == "all_max":
+        bd["seq_lens"] = torch.full((batch,), 50, dtype=torch.int64)
+    else:
+        bd["seq_lens"] = torch.tensor([1, 50, 2, 49, 25, 7], dtype=torch.int64)
+    pos = torch.arange(50).unsqueeze(0)
+    bd["ids"] = torch.where(pos < bd["seq_lens"].unsqueeze(1), bd["ids"].clamp(max=VOCAB - 2), torch.full_like(bd["ids"], VOCAB - 1))
+    eng.set_batch(None, bd["ids"], bd["seq_lens"], bd["labels"])
+    p64 = _to64(p)
+    opt = O.TFAdam(O.trainable_names(p64), p64)
+    loss_ref, logits_ref, grads_ref = O.train_step("text", p64, opt, 1e-3, bd, None)
+    eng.train_step(1e-3)
+    torch.cuda.synchronize()
+    assert row_rel_l2(eng.get_logits(), logits_ref) <= 1e-3
+    assert abs(eng.total_loss() - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
+    g_l2, _ = _grad_errors(lambda n: eng.tensor(n, "grads"), grads_ref, O.trainable_names(p64))
+    assert g_l2 <= 1e-3, g_l2
+
+
+def test_batch_of_one_and_odd_batch():
+    """BN over a single image (M = H*W rows) and a batch that is not a multiple of anything: ragged last tiles everywhere"""
+    for batch in (1, 5):
+        eng, p, bd, mask = make("image", batch, "bf16x3")
+        p64, bd64 = _to64(p), _to64(bd)
+        opt = O.TFAdam(O.trainable_names(p64), p64)
+        loss_ref, logits_ref, _ = O.train_step("image", p64, opt, 1e-3, bd64, mask.double())
+        eng.train_step(1e-3)
+        torch.cuda.synchronize()
+        assert row_rel_l2(eng.get_logits(), logits_ref) <= 1e-3, batch
+        assert abs(eng.total_loss() - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))

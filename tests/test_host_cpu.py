@@ -237,3 +237,12 @@ def test_two_clone_gradient_mean_equals_full_batch_without_bn():
     full, a, b = grads(slice(0, 8)), grads(slice(0, 4)), grads(slice(4, 8))
     for n in names:
         assert torch.allclose((a[n] + b[n]) / 2, full[n], rtol=1e-4, atol=1e-7), n
+
+
+def test_unknown_final_endpoint_raises_like_the_reference():
+    """image_model/inception_v1.py:251 raises ValueError('Unknown final endpoint %s'); the engine checks it before touching CUDA"""
+    from tumblr_emotions_b200.engine import Engine
+    with pytest.raises(ValueError, match="Unknown final endpoint"):
+        Engine(model="image", batch=2, final_endpoint="Mixed_9z")
+    with pytest.raises(ValueError, match="unknown model"):
+        Engine(model="audio", batch=2)

@@ -264,3 +264,18 @@ def test_stem_conv_space_to_depth_matches_oracle(K, b, hw, n):
     close(c, ref, 1e-4, "s2d stem conv")
     close(stats[:n], ref.sum(0), 1e-4, "stats sum")
     close(stats[n:], (ref * ref).sum(0), 1e-4, "stats sumsq")
+
+
+def test_empty_inputs_are_no_ops(K):
+    """M = 0 / N = 0: every entry point returns success without launching (no-op), as TF ops do on empty batches"""
+    a = K.SView(K.new_split((8,), 64, DEV))
+    w = K.SView(K.new_split((16,), 64, DEV))
+    c = torch.full((8, 16), 7.0, device=DEV)
+    K.conv_bf16x3(a, 0, 1, 1, 64, 1, w, 16, K.View(c))
+    K.bn_apply_relu_split(K.View(c), torch.zeros(16, device=DEV), torch.ones(16, device=DEV), 1e-3, torch.zeros(16, device=DEV),
+                          K.SView(K.new_split((8,), 16, DEV)))
+    from tumblr_emotions_b200._lib import lib
+    lib().maxpool_bwd(0, 4, 0, 0, 7, 7, 8, 3, 1, 1, 1, 7, 7, 0, 8, 0, 0)
+    lib().embedding_gather(0, 10, 50, 0, 0, 50, 0, 64, 0)
+    torch.cuda.synchronize()
+    assert float(c.min()) == 7.0
