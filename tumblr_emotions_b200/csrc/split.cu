@@ -306,6 +306,77 @@ __global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* 
   }
 }
 
+// Fused tail of a conv whose only consumer is a max pool (the stem, image_model/inception_v1.py:63-67): y = maxpool(relu(bn(z))) =
+// relu(bn(maxpool(z))) because bn (rstd > 0) and relu are monotone - pool the raw fp32 pre-activations, then normalise only the
+// pooled values and write them as split planes.  The full-resolution activation is never materialised (saves one write and
+// one read of it).  `stats` != NULL fuses ds_bn_finalize as in bn_apply_split_kernel.  One CTA per output row.
+template <int K>
+__global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t B, int h, int w,
+                                                                    int c4, int stride, int pad_t, int pad_l, int ho, int wo,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    float eps, const float* __restrict__ beta, int flags,
+                                                                    const double* __restrict__ stats, int64_t stats_ld, int64_t m_rows,
+                                                                    float* mean_out, float* rstd_out, float* moving_mean,
+                                                                    float* moving_var, float momentum,
+                                                                    uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy) {
+  const int64_t b = blockIdx.x / (uint32_t)ho;
+  const int p = (int)(blockIdx.x - b * ho);
+  const uint32_t row_items = (uint32_t)wo * (uint32_t)c4;
+  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
+    const int q = (int)(i / (uint32_t)c4);
+    const int col = (int)(i - (uint32_t)q * (uint32_t)c4) * 4;
+    const int ih0 = p * stride - pad_t, iw0 = q * stride - pad_l;
+    float4 v[K * K];
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+      for (int sx = 0; sx < K; ++sx) {
+        const int ih = ih0 + r, iw = iw0 + sx;
+        const bool ok = ih >= 0 && ih < h && iw >= 0 && iw < w;
+        v[r * K + sx] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (ok) v[r * K + sx] = __ldg(reinterpret_cast<const float4*>(z + ((b * h + ih) * (int64_t)w + iw) * ldz + col));
+      }
+    float4 mx = v[0];
+#pragma unroll
+    for (int t = 1; t < K * K; ++t) {
+      mx.x = fmaxf(mx.x, v[t].x); mx.y = fmaxf(mx.y, v[t].y); mx.z = fmaxf(mx.z, v[t].z); mx.w = fmaxf(mx.w, v[t].w);
+    }
+    float mu[4], rs[4];
+    if (stats) {
+      const double inv_m = 1.0 / (double)m_rows;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double mean_d = stats[col + j] * inv_m;
+        double var_d = stats[stats_ld + col + j] * inv_m - mean_d * mean_d;
+        if (var_d < 0) var_d = 0;
+        const float var_f = (float)var_d;
+        mu[j] = (float)mean_d; rs[j] = rsqrtf(var_f + eps);
+        if (blockIdx.x == 0 && q == 0) {         // one thread per channel group publishes the statistics
+          mean_out[col + j] = mu[j]; rstd_out[col + j] = rs[j];
+          if (moving_mean) {
+            float mv_in = var_f;
+            if ((flags & DS_BN_UNBIASED) && m_rows > 1) mv_in = var_f * (float)((double)m_rows / (double)(m_rows - 1));
+            moving_mean[col + j] -= momentum * (moving_mean[col + j] - mu[j]);
+            moving_var[col + j] -= momentum * (moving_var[col + j] - mv_in);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mu[j] = __ldg(mean + col + j);
+        rs[j] = __ldg(rstd + col + j);
+        if (flags & DS_BN_USE_VAR) rs[j] = rsqrtf(rs[j] + eps);
+      }
+    }
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float out[4] = {fmaxf((mx.x - mu[0]) * rs[0] + be.x, 0.f), fmaxf((mx.y - mu[1]) * rs[1] + be.y, 0.f),
+                    fmaxf((mx.z - mu[2]) * rs[2] + be.z, 0.f), fmaxf((mx.w - mu[3]) * rs[3] + be.w, 0.f)};
+    const int64_t o = ((b * ho + p) * (int64_t)wo + q);
+    ds::store4_split(y_hi + o * ldy + col, y_lo + o * ldy + col, out);
+  }
+}
+
 // 3x3 / stride 1 / pad 1 (the in-block pools): a thread produces a 2x2 patch of outputs for 4 channels from the 4x4 input
 // patch it loads once - 16 tap loads per 4 outputs instead of 36 (the kernel is bound by L1 bandwidth, not HBM).
 // Taps are visited in row-major order, so every output still sees its window in TF scan order (first maximum wins).
@@ -655,6 +726,26 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
   else
     maxpool_fwd_split_kernel<2><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
                                                                                 pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t,
+                             int pad_l, int64_t ho, int64_t wo, const float* mean, const float* rstd, float eps, const float* beta,
+                             int flags, const double* stats, int64_t stats_ld, float* mean_out, float* rstd_out, float* moving_mean,
+                             float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, void* stream) {
+  DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
+  DS_REQUIRE(k == 2 || k == 3, "2x2 and 3x3 windows");
+  DS_REQUIRE(stats ? (mean_out && rstd_out) : (mean && rstd), "either batch sums (+ outputs) or mean / rstd");
+  DS_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "moving_mean / moving_var go together");
+  if (batch * ho * wo * c == 0) return 0;
+  const int64_t m_rows = batch * h * w;
+#define DS_GO(KK)                                                                                                                  \
+  maxpool_bn_relu_split_kernel<KK><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(z, ldz, batch, (int)h, (int)w, (int)(c / 4), stride, \
+      pad_t, pad_l, (int)ho, (int)wo, mean, rstd, eps, beta, flags, stats, stats_ld, m_rows, mean_out, rstd_out, moving_mean, moving_var, \
+      momentum, y_hi, y_lo, ldy)
+  if (k == 3) DS_GO(3); else DS_GO(2);
+#undef DS_GO
   DS_LAUNCH_CHECK();
   return 0;
 }

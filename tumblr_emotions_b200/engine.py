@@ -58,6 +58,7 @@ class ConvUnit:
         self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
         self.split = eng.split
         self.dbeta_pool = None
+        self.fused_pool = None          # PoolNode that applies this unit's BN + ReLU on the pooled map (frozen stem)
         self.tc = self.split and stride == 1 and k in (1, 3) and cin % 8 == 0
         self.Z = eng.new(self.M, self.N)
         off = eng.bn_cursor
@@ -148,6 +149,8 @@ class ConvUnit:
                 ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
             if train:
                 ops.colstats(Zv, self.stats)
+        if self.fused_pool is not None:
+            return                        # BN + ReLU are applied by the pool node on the pooled pre-activations
         if train and self.split:      # finalize (mean / rstd / moving averages) fused into the apply launch of each segment
             fl = ops.BN_UNBIASED if e.unbiased_moving_var else 0
             for (c, n), out in zip(self.segs, self.outs):
@@ -225,10 +228,23 @@ class PoolNode:
         self.h_out, self.pad, _ = same_pad(h_in, k, stride)
         self.x, self.y, self.dx, self.dy, self.dx_accumulate = x, y, dx, dy, dx_accumulate
         self.skip_bwd = False           # set when the producer takes its beta gradient from the pooled map instead
+        self.fused_unit = None          # ConvUnit whose BN + ReLU this node applies after pooling (frozen stem)
         self.argmax = torch.empty(eng.batch * self.h_out * self.h_out * c, dtype=torch.uint8, device=eng.device)
 
     def fwd(self, train):
         B = self.eng.batch
+        u = self.fused_unit
+        if u is not None:      # y = maxpool(relu(bn(z))) = relu(bn(maxpool(z))): pool the producer's raw pre-activations
+            e = self.eng
+            if train:
+                ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
+                                          self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_UNBIASED if e.unbiased_moving_var else 0,
+                                          stats=u.stats, stats_ld=u.N, mean_out=u.mean, rstd_out=u.rstd, moving_mean=u.mov_mean,
+                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY)
+            else:
+                ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
+                                          self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_USE_VAR, mean=u.mov_mean, rstd=u.mov_var)
+            return
         f = ops.maxpool_fwd_split if self.eng.split else ops.maxpool_fwd
         f(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out, self.y,
           self.argmax if (train and not self.skip_bwd) else None)
@@ -351,8 +367,11 @@ class Engine:
                 dout = self.new(B, ho, ho, c) if tr else None
                 node = PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None)
                 prev = self.nodes[-1] if self.nodes else None
-                if tr and self.split and isinstance(prev, ConvUnit) and prev.dx is None and not prev.trainable:
-                    prev.dbeta_pool, node.skip_bwd = node, True
+                if (self.split and isinstance(prev, ConvUnit) and len(prev.outs) == 1 and prev.outs[0] is act and prev.dx is None
+                        and not prev.trainable):
+                    prev.fused_pool, node.fused_unit = node, prev            # nobody else reads the full-resolution activation
+                    if tr:
+                        prev.dbeta_pool, node.skip_bwd = node, True
                 self.nodes.append(node)
                 act, dact, h = vout, View(dout) if tr else None, ho
             else:
