@@ -122,11 +122,14 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
 /* y = maxpool(relu(bn(z))) computed as relu(bn(maxpool(z))) (monotone), z fp32 NHWC pre-activations, y split planes: the tail
  * of a conv whose only consumer is a max pool (the stem, image_model/inception_v1.py:63-67).  Train mode: pass the fp64 batch sums
  * `stats` (ds_bn_finalize is fused: mean_out / rstd_out are published, the moving averages updated); inference: pass mean /
- * variance with DS_BN_USE_VAR. */
+ * variance with DS_BN_USE_VAR.  `argmax` (optional, for ds_maxpool_bwd) records the first maximum of z in scan order: it equals
+ * the first maximum of relu(bn(z)) whenever the maximum is positive; in an all-non-positive window TF would pick the first element
+ * and this kernel may pick another, but the gradient routed there is multiplied by relu'(.) = 0 in the BN backward either way. */
 int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t,
                              int pad_l, int64_t ho, int64_t wo, const float* mean, const float* rstd, float eps, const float* beta,
                              int flags, const double* stats, int64_t stats_ld, float* mean_out, float* rstd_out, float* moving_mean,
-                             float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, void* stream);
+                             float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, uint8_t* argmax,
+                             void* stream);
 int ds_avgpool_dropout_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t hw, int64_t c,
                                  const float* mask, float inv_keep, float* out, int64_t ldo, void* stream);
 

@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
                                                                     const double* __restrict__ stats, int64_t stats_ld, int64_t m_rows,
                                                                     float* mean_out, float* rstd_out, float* moving_mean,
                                                                     float* moving_var, float momentum,
-                                                                    uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy) {
+                                                                    uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
+                                                                    uint8_t* __restrict__ argmax) {
   const int64_t b = blockIdx.x / (uint32_t)ho;
   const int p = (int)(blockIdx.x - b * ho);
   const uint32_t row_items = (uint32_t)wo * (uint32_t)c4;
@@ -337,9 +338,22 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
         if (ok) v[r * K + sx] = __ldg(reinterpret_cast<const float4*>(z + ((b * h + ih) * (int64_t)w + iw) * ldz + col));
       }
     float4 mx = v[0];
+    if (argmax) {      // first maximum in scan order (TF MaxPoolGrad); see ds_maxpool_bn_relu_split for why ties at <= 0 do not matter
+      uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-    for (int t = 1; t < K * K; ++t) {
-      mx.x = fmaxf(mx.x, v[t].x); mx.y = fmaxf(mx.y, v[t].y); mx.z = fmaxf(mx.z, v[t].z); mx.w = fmaxf(mx.w, v[t].w);
+      for (int t = 1; t < K * K; ++t) {
+        if (v[t].x > mx.x) { mx.x = v[t].x; a0 = t; }
+        if (v[t].y > mx.y) { mx.y = v[t].y; a1 = t; }
+        if (v[t].z > mx.z) { mx.z = v[t].z; a2 = t; }
+        if (v[t].w > mx.w) { mx.w = v[t].w; a3 = t; }
+      }
+      const int64_t oa = ((b * ho + p) * (int64_t)wo + q);
+      *reinterpret_cast<uint32_t*>(argmax + (oa * c4 + (col >> 2)) * 4) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+    } else {
+#pragma unroll
+      for (int t = 1; t < K * K; ++t) {
+        mx.x = fmaxf(mx.x, v[t].x); mx.y = fmaxf(mx.y, v[t].y); mx.z = fmaxf(mx.z, v[t].z); mx.w = fmaxf(mx.w, v[t].w);
+      }
     }
     float mu[4], rs[4];
     if (stats) {
@@ -733,7 +747,8 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
 int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t,
                              int pad_l, int64_t ho, int64_t wo, const float* mean, const float* rstd, float eps, const float* beta,
                              int flags, const double* stats, int64_t stats_ld, float* mean_out, float* rstd_out, float* moving_mean,
-                             float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, void* stream) {
+                             float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, uint8_t* argmax,
+                             void* stream) {
   DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE(k == 2 || k == 3, "2x2 and 3x3 windows");
   DS_REQUIRE(stats ? (mean_out && rstd_out) : (mean && rstd), "either batch sums (+ outputs) or mean / rstd");
@@ -743,7 +758,7 @@ int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t
 #define DS_GO(KK)                                                                                                                  \
   maxpool_bn_relu_split_kernel<KK><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(z, ldz, batch, (int)h, (int)w, (int)(c / 4), stride, \
       pad_t, pad_l, (int)ho, (int)wo, mean, rstd, eps, beta, flags, stats, stats_ld, m_rows, mean_out, rstd_out, moving_mean, moving_var, \
-      momentum, y_hi, y_lo, ldy)
+      momentum, y_hi, y_lo, ldy, argmax)
   if (k == 3) DS_GO(3); else DS_GO(2);
 #undef DS_GO
   DS_LAUNCH_CHECK();

@@ -240,7 +240,7 @@ class PoolNode:
                 ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
                                           self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_UNBIASED if e.unbiased_moving_var else 0,
                                           stats=u.stats, stats_ld=u.N, mean_out=u.mean, rstd_out=u.rstd, moving_mean=u.mov_mean,
-                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY)
+                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY, argmax=None if self.skip_bwd else self.argmax)
             else:
                 ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
                                           self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_USE_VAR, mean=u.mov_mean, rstd=u.mov_var)
@@ -367,10 +367,9 @@ class Engine:
                 dout = self.new(B, ho, ho, c) if tr else None
                 node = PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None)
                 prev = self.nodes[-1] if self.nodes else None
-                if (self.split and isinstance(prev, ConvUnit) and len(prev.outs) == 1 and prev.outs[0] is act and prev.dx is None
-                        and not prev.trainable):
+                if self.split and isinstance(prev, ConvUnit) and len(prev.outs) == 1 and prev.outs[0] is act:
                     prev.fused_pool, node.fused_unit = node, prev            # nobody else reads the full-resolution activation
-                    if tr:
+                    if tr and prev.dx is None and not prev.trainable:        # frozen stem: no backward through the pool either
                         prev.dbeta_pool, node.skip_bwd = node, True
                 self.nodes.append(node)
                 act, dact, h = vout, View(dout) if tr else None, ho

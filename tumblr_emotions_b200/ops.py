@@ -174,10 +174,11 @@ def maxpool_fwd_split(x: SView, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo,
 
 
 def maxpool_bn_relu_split(z: View, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, beta, y: SView, eps, flags=0, mean=None, rstd=None,
-                          stats=None, stats_ld=0, mean_out=None, rstd_out=None, moving_mean=None, moving_var=None, momentum=0.0):
+                          stats=None, stats_ld=0, mean_out=None, rstd_out=None, moving_mean=None, moving_var=None, momentum=0.0,
+                          argmax=None):
     lib().maxpool_bn_relu_split(z.ptr, z.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, _p(mean), _p(rstd), eps, _p(beta), flags,
                                 _p(stats), stats_ld, _p(mean_out), _p(rstd_out), _p(moving_mean), _p(moving_var), momentum, y.ptr,
-                                y.lo_ptr, y.ld, _stream())
+                                y.lo_ptr, y.ld, _p(argmax), _stream())
 
 
 def avgpool_dropout_fwd_split(x: SView, batch, hw, c, mask, inv_keep, out: View):
