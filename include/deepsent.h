@@ -111,9 +111,18 @@ int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, in
                                const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
 /* sums[c] += sum_rows dy[row,c] * [y[row,c] > 0] on a max-pooled map: the beta gradient of a frozen conv+BN+ReLU whose only
- * consumer is that max pool (the stem, image_model/inception_v1.py:63-67), without differentiating through the pool */
+ * consumer is that max pool (the stem, image_model/inception_v1.py:63-67), without differentiating through the pool.
+ * With beta != NULL it also adds sum dy * [y > 0] * (y - beta[c]) into sums[sums_ld + c] (y - beta is xhat where y > 0): both
+ * BN-backward reductions of a conv -> BN -> ReLU -> max pool chain come off the pooled map. */
 int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldy, int64_t m, int64_t n,
-                           double* sums, void* stream);
+                           double* sums, const float* beta, int64_t sums_ld, void* stream);
+/* ds_maxpool_bwd + ds_bn_relu_bwd_apply_split in one pass for such a chain (Conv2d_2c -> MaxPool_3a, image_model/inception_v1.py:74-79):
+ * dz[pixel] = rstd * (g - sum(g)/m - xhat * sum(g*xhat)/m) with g = [bn(z) > 0] * (sum of the pooled gradients dyp whose recorded
+ * argmax is this pixel); the routed full-resolution gradient is never materialised. */
+int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t* argmax, const float* z, int64_t ldz, int64_t batch,
+                                  int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
+                                  const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
+                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
 /* dbeta[c] = sums[c] (the frozen stem needs no dz: only its beta gradient) */
 int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream);
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,

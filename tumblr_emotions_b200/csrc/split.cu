@@ -580,37 +580,116 @@ __global__ void __launch_bounds__(256) s2d_split_kernel(const float* __restrict_
 // sums[c] += sum_rows dy[row, c] * [y[row, c] > 0]: the beta gradient of a frozen conv + BN + ReLU whose only consumer is a max
 // pool, read off the *pooled* map (a pooled value is > 0 exactly when the element it was taken from passed the ReLU, and each
 // pool output routes its gradient to exactly one element) - no need to differentiate through the pool (the stem).
+// With `beta` != NULL it also accumulates sums[sums_ld + c] += sum dy * [y > 0] * (y - beta[c]): y - beta is xhat wherever y > 0
+// (scale-free BN), so both BN-backward reductions of the conv come off the pooled map.
 __global__ void __launch_bounds__(256) masked_colsum_split_kernel(const float* __restrict__ dy, int64_t lddy,
                                                                   const uint16_t* __restrict__ y_hi, const uint16_t* __restrict__ y_lo,
                                                                   int64_t ldy, int64_t M, int64_t N, double* __restrict__ sums,
-                                                                  int rows_per_cta) {
+                                                                  int rows_per_cta, const float* __restrict__ beta, int64_t sums_ld) {
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = min(M, r0 + rows_per_cta);
-  float s[4] = {0, 0, 0, 0};
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (col < N) {
+    float be[4] = {0, 0, 0, 0};
+    if (beta) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + col)); be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w; }
 #pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += rl) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + col));
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
       float yv[4];
       ds::load4_split(y_hi + r * ldy + col, y_lo + r * ldy + col, yv);
-      s[0] += yv[0] > 0.f ? g.x : 0.f; s[1] += yv[1] > 0.f ? g.y : 0.f;
-      s[2] += yv[2] > 0.f ? g.z : 0.f; s[3] += yv[3] > 0.f ? g.w : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = yv[j] > 0.f ? gg[j] : 0.f;
+        s[j] += g;
+        q[j] = fmaf(g, yv[j] - be[j], q[j]);
+      }
     }
   }
-  __shared__ float red[256 * 4];
+  __shared__ float red[256 * 8];
   const int t = threadIdx.y * cgs + threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) red[t * 4 + i] = s[i];
+  for (int i = 0; i < 4; ++i) { red[t * 8 + i] = s[i]; red[t * 8 + 4 + i] = q[i]; }
   __syncthreads();
-  if (threadIdx.y == 0 && col < N) {
-    double a[4] = {0, 0, 0, 0};
-    for (int y = 0; y < rl; ++y)
+  if (col < N) {
+    for (int v = threadIdx.y; v < (beta ? 8 : 4); v += rl) {
+      double a = 0.0;
+      for (int y = 0; y < rl; ++y) a += red[(y * cgs + threadIdx.x) * 8 + v];
+      atomicAdd(sums + (v < 4 ? 0 : sums_ld) + col + (v & 3), a);
+    }
+  }
+}
+
+// Backward of conv -> BN -> ReLU -> max pool when the pool is the conv's only consumer: the pool's gradient routing (gather over the
+// recorded argmax, as in maxpool_bwd_kernel) and the BN/ReLU backward  dz = rstd * (g - sum(g)/m - xhat * sum(g*xhat)/m)  in one pass
+// over the full-resolution pre-activations; the routed gradient is never materialised.  One CTA per input row, 4 channels per thread.
+template <int K, int S>
+__global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const float* __restrict__ dyp, int64_t lddy,
+                                                                         const uint8_t* __restrict__ argmax, const float* __restrict__ z,
+                                                                         int64_t ldz, int64_t B, int h, int w, int c4, int pad_t, int pad_l,
+                                                                         int ho, int wo, const float* __restrict__ mean,
+                                                                         const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                                         const double* __restrict__ sums, int64_t sums_ld,
+                                                                         uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo,
+                                                                         int64_t lddz, float* dbeta) {
+  constexpr int NW = (K + S - 1) / S;
+  const int64_t b = blockIdx.x / (uint32_t)h;
+  const int ih = (int)(blockIdx.x - b * h);
+  const double inv_m = 1.0 / ((double)B * h * w);
+  const uint32_t row_items = (uint32_t)w * (uint32_t)c4;
+  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
+    const int iw = (int)(i / (uint32_t)c4);
+    const int cg = (int)(i - (uint32_t)iw * (uint32_t)c4);
+    const int col = cg * 4;
+    const int p_hi = (ih + pad_t) / S, q_hi = (iw + pad_l) / S;
+    const int64_t pix = (b * h + ih) * (int64_t)w + iw;
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(z + pix * ldz + col));
+    uint32_t mk[NW * NW];
+    int64_t oo[NW * NW];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] += red[(y * cgs + threadIdx.x) * 4 + i];
+    for (int a = 0; a < NW; ++a)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(sums + col + i, a[i]);
+      for (int c = 0; c < NW; ++c) {
+        const int n = a * NW + c;
+        const int p = p_hi - a, q = q_hi - c;
+        const int r = ih + pad_t - p * S, sx = iw + pad_l - q * S;
+        const bool v = p >= 0 && p < ho && q >= 0 && q < wo && r < K && sx < K;
+        const int64_t o = ((b * ho + (v ? p : 0)) * (int64_t)wo + (v ? q : 0));
+        oo[n] = o;
+        const uint32_t me4 = v ? (uint32_t)(r * K + sx) * 0x01010101u : 0xfefefefeu;
+        mk[n] = __vcmpeq4(__ldg(reinterpret_cast<const uint32_t*>(argmax + (o * c4 + cg) * 4)), me4);
+      }
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < NW * NW; ++n) {
+      if (mk[n]) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(dyp + oo[n] * lddy + col));
+        g[0] += (mk[n] & 0x000000ffu) ? gv.x : 0.f;
+        g[1] += (mk[n] & 0x0000ff00u) ? gv.y : 0.f;
+        g[2] += (mk[n] & 0x00ff0000u) ? gv.z : 0.f;
+        g[3] += (mk[n] & 0xff000000u) ? gv.w : 0.f;
+      }
+    }
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (zz[j] - mu[j]) * rs[j];
+      const float gm = (xh + be[j] > 0.f) ? g[j] : 0.f;
+      const float m1 = (float)(sums[col + j] * inv_m), m2 = (float)(sums[sums_ld + col + j] * inv_m);
+      out[j] = rs[j] * (gm - m1 - xh * m2);
+    }
+    ds::store4_split(dz_hi + pix * lddz + col, dz_lo + pix * lddz + col, out);
+    if (dbeta && blockIdx.x == 0 && iw == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dbeta[col + j] = (float)sums[col + j];
+    }
   }
 }
 
@@ -799,7 +878,7 @@ int ds_s2d_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t pi
 }
 
 int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, const uint16_t* y_lo, int64_t ldy, int64_t m, int64_t n,
-                           double* sums, void* stream) {
+                           double* sums, const float* beta, int64_t sums_ld, void* stream) {
   DS_REQUIRE(n % 4 == 0 && lddy % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
   int cgs = (int)std::min<int64_t>(n / 4, 32), pw = 1;
@@ -809,7 +888,27 @@ int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, 
   int64_t rows = ds::cdiv(m, std::max<int64_t>(1, (148 * 24) / gx));
   rows = std::max<int64_t>(256, ds::cdiv(rows, 64) * 64);
   dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
-  masked_colsum_split_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, y_hi, y_lo, ldy, m, n, sums, (int)rows);
+  masked_colsum_split_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, y_hi, y_lo, ldy, m, n, sums, (int)rows, beta, sums_ld);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t* argmax, const float* z, int64_t ldz, int64_t batch,
+                                  int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
+                                  const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
+                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream) {
+  DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0 && lddz % 4 == 0, "channel counts must be multiples of 4");
+  DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dyp) & 15) == 0, "16-byte alignment");
+  if (batch * h * w * c == 0) return 0;
+  const unsigned blocks = (unsigned)(batch * h);
+#define DS_GO(KK, SS)                                                                                                              \
+  maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, 256, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
+      (int)(c / 4), pad_t, pad_l, (int)ho, (int)wo, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta)
+  if (k == 3 && stride == 2) DS_GO(3, 2);
+  else if (k == 2 && stride == 2) DS_GO(2, 2);
+  else if (k == 3 && stride == 1) DS_GO(3, 1);
+  else return ds::fail("ds_maxpool_bwd_bn_apply_split: unsupported window %dx%d stride %d", k, k, stride);
+#undef DS_GO
   DS_LAUNCH_CHECK();
   return 0;
 }

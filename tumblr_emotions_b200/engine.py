@@ -173,6 +173,20 @@ class ConvUnit:
             ops.masked_colsum_split(self.dbeta_pool.dy, self.dbeta_pool.y, self.sums)
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
+        pool = self.fused_pool
+        if pool is not None and self.split:
+            # conv -> BN -> ReLU -> max pool chain: both BN reductions come off the pooled map, and the pool's gradient routing is
+            # fused into the BN backward pass over the full-resolution pre-activations
+            ops.masked_colsum_split(pool.dy, pool.y, self.sums, beta=self.beta, sums_ld=self.N)
+            dZ = SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
+            ops.maxpool_bwd_bn_apply_split(pool.dy, pool.argmax, Zv, B, pool.h_in, pool.h_in, pool.c, pool.k, pool.stride, pool.pad, pool.pad,
+                                           pool.h_out, pool.h_out, self.mean, self.rstd, self.beta, self.sums, self.N, dZ, self.dbeta)
+            if self.trainable:
+                self._wgrad(dZ)
+            if self.dx is not None:
+                fl = ops.EPI_ACCUMULATE if self.dx_accumulate else 0
+                ops.conv_bf16x3(dZ, B, h, h, self.N, self.k, self.w_dgrad, self.cin, self.dx, flags=fl)
+            return
         for (c, n), dy in zip(self.segs, self.douts):
             ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
                                    self.N, fast=self.split)
@@ -240,7 +254,7 @@ class PoolNode:
                 ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
                                           self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_UNBIASED if e.unbiased_moving_var else 0,
                                           stats=u.stats, stats_ld=u.N, mean_out=u.mean, rstd_out=u.rstd, moving_mean=u.mov_mean,
-                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY, argmax=None if self.skip_bwd else self.argmax)
+                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY, argmax=None if u.dbeta_pool is not None else self.argmax)
             else:
                 ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
                                           self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_USE_VAR, mean=u.mov_mean, rstd=u.mov_var)
@@ -369,8 +383,10 @@ class Engine:
                 prev = self.nodes[-1] if self.nodes else None
                 if self.split and isinstance(prev, ConvUnit) and len(prev.outs) == 1 and prev.outs[0] is act:
                     prev.fused_pool, node.fused_unit = node, prev            # nobody else reads the full-resolution activation
-                    if tr and prev.dx is None and not prev.trainable:        # frozen stem: no backward through the pool either
-                        prev.dbeta_pool, node.skip_bwd = node, True
+                    if tr:
+                        node.skip_bwd = True                                 # the producer's backward consumes the pooled gradient
+                        if prev.dx is None and not prev.trainable:           # frozen stem: only its beta gradient is needed
+                            prev.dbeta_pool = node
                 self.nodes.append(node)
                 act, dact, h = vout, View(dout) if tr else None, ho
             else:

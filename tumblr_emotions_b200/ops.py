@@ -137,8 +137,14 @@ def conv_s2d_rows(s_hi: torch.Tensor, s_lo: torch.Tensor, batch, rows, wout, pit
                         EPI_STATS if stats is not None else 0, _stream())
 
 
-def masked_colsum_split(dy: View, y: SView, sums):
-    lib().masked_colsum_split(dy.ptr, dy.ld, y.ptr, y.lo_ptr, y.ld, y.rows, y.cols, _p(sums), _stream())
+def masked_colsum_split(dy: View, y: SView, sums, beta=None, sums_ld=0):
+    lib().masked_colsum_split(dy.ptr, dy.ld, y.ptr, y.lo_ptr, y.ld, y.rows, y.cols, _p(sums), _p(beta), sums_ld, _stream())
+
+
+def maxpool_bwd_bn_apply_split(dyp: View, argmax, z: View, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, mean, rstd, beta, sums, sums_ld,
+                               dz: SView, dbeta):
+    lib().maxpool_bwd_bn_apply_split(dyp.ptr, dyp.ld, _p(argmax), z.ptr, z.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, _p(mean),
+                                     _p(rstd), _p(beta), _p(sums), sums_ld, dz.ptr, dz.lo_ptr, dz.ld, _p(dbeta), _stream())
 
 
 def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None, fwd_rs: int = 0):
