@@ -122,7 +122,7 @@ int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, 
 int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t* argmax, const float* z, int64_t ldz, int64_t batch,
                                   int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
                                   const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
-                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
+                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, int64_t arg_ld, void* stream);
 /* dbeta[c] = sums[c] (the frozen stem needs no dz: only its beta gradient) */
 int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream);
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,
@@ -133,12 +133,15 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
  * `stats` (ds_bn_finalize is fused: mean_out / rstd_out are published, the moving averages updated); inference: pass mean /
  * variance with DS_BN_USE_VAR.  `argmax` (optional, for ds_maxpool_bwd) records the first maximum of z in scan order: it equals
  * the first maximum of relu(bn(z)) whenever the maximum is positive; in an all-non-positive window TF would pick the first element
- * and this kernel may pick another, but the gradient routed there is multiplied by relu'(.) = 0 in the BN backward either way. */
+ * and this kernel may pick another, but the gradient routed there is multiplied by relu'(.) = 0 in the BN backward either way.
+ * z / y / argmax may be channel slices of wider buffers (ldz, ldy, arg_ld = bytes per pixel of the argmax map, 0 = c): the four
+ * branches of an inception block whose concat feeds only a max pool (Mixed_3c -> MaxPool_4a, Mixed_4f -> MaxPool_5a) each get
+ * their own launch. */
 int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t,
                              int pad_l, int64_t ho, int64_t wo, const float* mean, const float* rstd, float eps, const float* beta,
                              int flags, const double* stats, int64_t stats_ld, float* mean_out, float* rstd_out, float* moving_mean,
                              float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, uint8_t* argmax,
-                             void* stream);
+                             int64_t arg_ld, void* stream);
 int ds_avgpool_dropout_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t hw, int64_t c,
                                  const float* mask, float inv_keep, float* out, int64_t ldo, void* stream);
 

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
                                                                     float* mean_out, float* rstd_out, float* moving_mean,
                                                                     float* moving_var, float momentum,
                                                                     uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
-                                                                    uint8_t* __restrict__ argmax) {
+                                                                    uint8_t* __restrict__ argmax, int64_t arg_ld) {
   const int64_t b = blockIdx.x / (uint32_t)ho;
   const int p = (int)(blockIdx.x - b * ho);
   const uint32_t row_items = (uint32_t)wo * (uint32_t)c4;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
         if (v[t].w > mx.w) { mx.w = v[t].w; a3 = t; }
       }
       const int64_t oa = ((b * ho + p) * (int64_t)wo + q);
-      *reinterpret_cast<uint32_t*>(argmax + (oa * c4 + (col >> 2)) * 4) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+      *reinterpret_cast<uint32_t*>(argmax + oa * arg_ld + col) = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
     } else {
 #pragma unroll
       for (int t = 1; t < K * K; ++t) {
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
                                                                          const float* __restrict__ rstd, const float* __restrict__ beta,
                                                                          const double* __restrict__ sums, int64_t sums_ld,
                                                                          uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo,
-                                                                         int64_t lddz, float* dbeta) {
+                                                                         int64_t lddz, float* dbeta, int64_t arg_ld) {
   constexpr int NW = (K + S - 1) / S;
   const int64_t b = blockIdx.x / (uint32_t)h;
   const int ih = (int)(blockIdx.x - b * h);
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
         const int64_t o = ((b * ho + (v ? p : 0)) * (int64_t)wo + (v ? q : 0));
         oo[n] = o;
         const uint32_t me4 = v ? (uint32_t)(r * K + sx) * 0x01010101u : 0xfefefefeu;
-        mk[n] = __vcmpeq4(__ldg(reinterpret_cast<const uint32_t*>(argmax + (o * c4 + cg) * 4)), me4);
+        mk[n] = __vcmpeq4(__ldg(reinterpret_cast<const uint32_t*>(argmax + o * arg_ld + col)), me4);
       }
     float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -827,7 +827,7 @@ int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t
                              int pad_l, int64_t ho, int64_t wo, const float* mean, const float* rstd, float eps, const float* beta,
                              int flags, const double* stats, int64_t stats_ld, float* mean_out, float* rstd_out, float* moving_mean,
                              float* moving_var, float momentum, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, uint8_t* argmax,
-                             void* stream) {
+                             int64_t arg_ld, void* stream) {
   DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE(k == 2 || k == 3, "2x2 and 3x3 windows");
   DS_REQUIRE(stats ? (mean_out && rstd_out) : (mean && rstd), "either batch sums (+ outputs) or mean / rstd");
@@ -837,7 +837,7 @@ int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t
 #define DS_GO(KK)                                                                                                                  \
   maxpool_bn_relu_split_kernel<KK><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(z, ldz, batch, (int)h, (int)w, (int)(c / 4), stride, \
       pad_t, pad_l, (int)ho, (int)wo, mean, rstd, eps, beta, flags, stats, stats_ld, m_rows, mean_out, rstd_out, moving_mean, moving_var, \
-      momentum, y_hi, y_lo, ldy, argmax)
+      momentum, y_hi, y_lo, ldy, argmax, arg_ld > 0 ? arg_ld : c)
   if (k == 3) DS_GO(3); else DS_GO(2);
 #undef DS_GO
   DS_LAUNCH_CHECK();
@@ -896,14 +896,14 @@ int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, 
 int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t* argmax, const float* z, int64_t ldz, int64_t batch,
                                   int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
                                   const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
-                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream) {
+                                  uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, int64_t arg_ld, void* stream) {
   DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0 && lddz % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dyp) & 15) == 0, "16-byte alignment");
   if (batch * h * w * c == 0) return 0;
   const unsigned blocks = (unsigned)(batch * h);
 #define DS_GO(KK, SS)                                                                                                              \
   maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, 256, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
-      (int)(c / 4), pad_t, pad_l, (int)ho, (int)wo, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta)
+      (int)(c / 4), pad_t, pad_l, (int)ho, (int)wo, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta, arg_ld > 0 ? arg_ld : c)
   if (k == 3 && stride == 2) DS_GO(3, 2);
   else if (k == 2 && stride == 2) DS_GO(2, 2);
   else if (k == 3 && stride == 1) DS_GO(3, 1);

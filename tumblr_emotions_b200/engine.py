@@ -57,8 +57,10 @@ class ConvUnit:
         self.M = eng.batch * self.h_out * self.h_out
         self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
         self.split = eng.split
-        self.dbeta_pool = None
-        self.fused_pool = None          # PoolNode that applies this unit's BN + ReLU on the pooled map (frozen stem)
+        self.dbeta_pool = None          # frozen stem: beta gradient straight from the pooled map, nothing else
+        # per output segment: (PoolNode, channel offset in the pooled map) when that segment feeds ONLY a max pool - then
+        # maxpool(relu(bn(z))) = relu(bn(maxpool(z))) and the pool node applies BN + ReLU on the pooled pre-activations
+        self.seg_pool = [None] * len(seg_cols)
         self.tc = self.split and stride == 1 and k in (1, 3) and cin % 8 == 0
         self.Z = eng.new(self.M, self.N)
         off = eng.bn_cursor
@@ -149,11 +151,11 @@ class ConvUnit:
                 ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
             if train:
                 ops.colstats(Zv, self.stats)
-        if self.fused_pool is not None:
-            return                        # BN + ReLU are applied by the pool node on the pooled pre-activations
         if train and self.split:      # finalize (mean / rstd / moving averages) fused into the apply launch of each segment
             fl = ops.BN_UNBIASED if e.unbiased_moving_var else 0
-            for (c, n), out in zip(self.segs, self.outs):
+            for (c, n), out, sp in zip(self.segs, self.outs, self.seg_pool):
+                if sp is not None:
+                    continue              # BN + ReLU are applied by the pool node on the pooled pre-activations
                 ops.bn_finalize_apply_relu_split(Zv.slice(c, n), self.stats[c:], self.N, self.mov_mean[c:c + n], self.mov_var[c:c + n],
                                                  1.0 - BN_DECAY, BN_EPS, self.beta[c:c + n], self.mean[c:c + n], self.rstd[c:c + n], out, fl)
         elif train:
@@ -162,8 +164,9 @@ class ConvUnit:
             for (c, n), out in zip(self.segs, self.outs):
                 self._apply(Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], out, 0)
         else:
-            for (c, n), out in zip(self.segs, self.outs):
-                self._apply(Zv.slice(c, n), self.mov_mean[c:c + n], self.mov_var[c:c + n], self.beta[c:c + n], out, ops.BN_USE_VAR)
+            for (c, n), out, sp in zip(self.segs, self.outs, self.seg_pool):
+                if sp is None:
+                    self._apply(Zv.slice(c, n), self.mov_mean[c:c + n], self.mov_var[c:c + n], self.beta[c:c + n], out, ops.BN_USE_VAR)
 
     # -- backward ------------------------------------------------------------------------------------------
     def bwd(self):
@@ -173,31 +176,28 @@ class ConvUnit:
             ops.masked_colsum_split(self.dbeta_pool.dy, self.dbeta_pool.y, self.sums)
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
-        pool = self.fused_pool
-        if pool is not None and self.split:
-            # conv -> BN -> ReLU -> max pool chain: both BN reductions come off the pooled map, and the pool's gradient routing is
-            # fused into the BN backward pass over the full-resolution pre-activations
-            ops.masked_colsum_split(pool.dy, pool.y, self.sums, beta=self.beta, sums_ld=self.N)
-            dZ = SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
-            ops.maxpool_bwd_bn_apply_split(pool.dy, pool.argmax, Zv, B, pool.h_in, pool.h_in, pool.c, pool.k, pool.stride, pool.pad, pool.pad,
-                                           pool.h_out, pool.h_out, self.mean, self.rstd, self.beta, self.sums, self.N, dZ, self.dbeta)
-            if self.trainable:
-                self._wgrad(dZ)
-            if self.dx is not None:
-                fl = ops.EPI_ACCUMULATE if self.dx_accumulate else 0
-                ops.conv_bf16x3(dZ, B, h, h, self.N, self.k, self.w_dgrad, self.cin, self.dx, flags=fl)
-            return
-        for (c, n), dy in zip(self.segs, self.douts):
-            ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
-                                   self.N, fast=self.split)
+        for (c, n), dy, sp in zip(self.segs, self.douts, self.seg_pool):
+            if sp is not None:   # conv -> BN -> ReLU -> max pool: both BN reductions come off the pooled map (y - beta = xhat where y > 0)
+                pool, off = sp
+                ops.masked_colsum_split(pool.dy.slice(off, n), pool.y.slice(off, n), self.sums[c:], beta=self.beta[c:c + n], sums_ld=self.N)
+            else:
+                ops.bn_relu_bwd_reduce(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:],
+                                       self.N, fast=self.split)
         if self.dx is None and not self.trainable:      # frozen stem: only its beta gradient is needed
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
         if self.split:
             dZ = SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
-            for (c, n), dy in zip(self.segs, self.douts):
-                ops.bn_relu_bwd_apply_split(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n],
-                                            self.sums[c:], self.N, dZ.slice(c, n), self.dbeta[c:c + n])
+            for (c, n), dy, sp in zip(self.segs, self.douts, self.seg_pool):
+                if sp is not None:   # the pool's gradient routing fused into the BN backward pass over the full-resolution pre-activations
+                    pool, off = sp
+                    ops.maxpool_bwd_bn_apply_split(pool.dy.slice(off, n), pool.argmax, Zv.slice(c, n), B, pool.h_in, pool.h_in, n, pool.k,
+                                                   pool.stride, pool.pad, pool.pad, pool.h_out, pool.h_out, self.mean[c:c + n],
+                                                   self.rstd[c:c + n], self.beta[c:c + n], self.sums[c:], self.N, dZ.slice(c, n),
+                                                   self.dbeta[c:c + n], arg_off=off, arg_ld=pool.c)
+                else:
+                    ops.bn_relu_bwd_apply_split(dy, Zv.slice(c, n), self.mean[c:c + n], self.rstd[c:c + n], self.beta[c:c + n],
+                                                self.sums[c:], self.N, dZ.slice(c, n), self.dbeta[c:c + n])
         else:
             dZ = Zv                                      # fp32 build: dz overwrites z in place
             for (c, n), dy in zip(self.segs, self.douts):
@@ -241,23 +241,27 @@ class PoolNode:
         self.eng, self.k, self.stride, self.c, self.h_in = eng, k, stride, c, h_in
         self.h_out, self.pad, _ = same_pad(h_in, k, stride)
         self.x, self.y, self.dx, self.dy, self.dx_accumulate = x, y, dx, dy, dx_accumulate
-        self.skip_bwd = False           # set when the producer takes its beta gradient from the pooled map instead
-        self.fused_unit = None          # ConvUnit whose BN + ReLU this node applies after pooling (frozen stem)
+        self.skip_bwd = False           # set when the producers' backward consumes the pooled gradient directly
+        self.fused = []                 # (ConvUnit, segment index, channel offset): producers whose BN + ReLU run here, after pooling
         self.argmax = torch.empty(eng.batch * self.h_out * self.h_out * c, dtype=torch.uint8, device=eng.device)
 
     def fwd(self, train):
         B = self.eng.batch
-        u = self.fused_unit
-        if u is not None:      # y = maxpool(relu(bn(z))) = relu(bn(maxpool(z))): pool the producer's raw pre-activations
+        if self.fused:      # y = maxpool(relu(bn(z))) = relu(bn(maxpool(z))): pool every producer's raw pre-activations
             e = self.eng
-            if train:
-                ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
-                                          self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_UNBIASED if e.unbiased_moving_var else 0,
-                                          stats=u.stats, stats_ld=u.N, mean_out=u.mean, rstd_out=u.rstd, moving_mean=u.mov_mean,
-                                          moving_var=u.mov_var, momentum=1.0 - BN_DECAY, argmax=None if u.dbeta_pool is not None else self.argmax)
-            else:
-                ops.maxpool_bn_relu_split(View(u.Z), B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out,
-                                          self.h_out, u.beta, self.y, BN_EPS, flags=ops.BN_USE_VAR, mean=u.mov_mean, rstd=u.mov_var)
+            for u, si, off in self.fused:
+                c, n = u.segs[si]
+                z, y = View(u.Z).slice(c, n), self.y.slice(off, n)
+                if train:
+                    ops.maxpool_bn_relu_split(z, B, self.h_in, self.h_in, n, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
+                                              u.beta[c:c + n], y, BN_EPS, flags=ops.BN_UNBIASED if e.unbiased_moving_var else 0,
+                                              stats=u.stats[c:], stats_ld=u.N, mean_out=u.mean[c:c + n], rstd_out=u.rstd[c:c + n],
+                                              moving_mean=u.mov_mean[c:c + n], moving_var=u.mov_var[c:c + n], momentum=1.0 - BN_DECAY,
+                                              argmax=None if u.dbeta_pool is not None else self.argmax, arg_off=off, arg_ld=self.c)
+                else:
+                    ops.maxpool_bn_relu_split(z, B, self.h_in, self.h_in, n, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out,
+                                              u.beta[c:c + n], y, BN_EPS, flags=ops.BN_USE_VAR, mean=u.mov_mean[c:c + n],
+                                              rstd=u.mov_var[c:c + n])
             return
         f = ops.maxpool_fwd_split if self.eng.split else ops.maxpool_fwd
         f(self.x, B, self.h_in, self.h_in, self.c, self.k, self.stride, self.pad, self.pad, self.h_out, self.h_out, self.y,
@@ -362,6 +366,7 @@ class Engine:
         B, tr = self.batch, self.training
         act = View(self.images)          # the stem reads the fp32 images
         dact = None                      # no gradient w.r.t. the images
+        producers = None                 # (unit, segment, channel offset) triples that wrote `act`, when known
         c, h = 3, IMAGE_SIZE
         for item in SEQUENCE:
             kind, name = item[0], item[1]
@@ -373,22 +378,22 @@ class Engine:
                 u = ConvUnit(self, ["InceptionV1/" + name], k, s, c, [cout], h, act, [vout], dact,
                              [View(dout)] if tr else [None], [(0, cout)])
                 self.units.append(u); self.nodes.append(u)
-                act, dact, c, h = vout, View(dout) if tr else None, cout, ho
+                act, dact, c, h, producers = vout, View(dout) if tr else None, cout, ho, [(u, 0, 0)]
             elif kind == "maxpool":
                 _, _, k, s = item
                 ho = same_pad(h, k, s)[0]
                 _, vout = self.act(B, ho, ho, c)
                 dout = self.new(B, ho, ho, c) if tr else None
                 node = PoolNode(self, k, s, c, h, act, vout, dact, View(dout) if tr else None)
-                prev = self.nodes[-1] if self.nodes else None
-                if self.split and isinstance(prev, ConvUnit) and len(prev.outs) == 1 and prev.outs[0] is act:
-                    prev.fused_pool, node.fused_unit = node, prev            # nobody else reads the full-resolution activation
-                    if tr:
-                        node.skip_bwd = True                                 # the producer's backward consumes the pooled gradient
-                        if prev.dx is None and not prev.trainable:           # frozen stem: only its beta gradient is needed
-                            prev.dbeta_pool = node
+                if self.split and producers:       # nobody but this pool reads the full-resolution activation
+                    for u, si, off in producers:
+                        u.seg_pool[si] = (node, off)
+                        node.fused.append((u, si, off))
+                        if tr and u.dx is None and not u.trainable:          # frozen stem: only its beta gradient is needed
+                            u.dbeta_pool = node
+                    node.skip_bwd = tr                                       # the producers' backward consumes the pooled gradient
                 self.nodes.append(node)
-                act, dact, h = vout, View(dout) if tr else None, ho
+                act, dact, h, producers = vout, View(dout) if tr else None, ho, None
             else:
                 c0, c1a, c1b, c2a, c2b, c3, _ = MIXED[name]
                 convs = mixed_convs(name, c)
@@ -413,6 +418,7 @@ class Engine:
                 # must come *before* the pool's accumulate in reverse order -> pool is listed before u1
                 self.nodes += [pool, u1, u2, u3, u4]
                 act, dact, c = vO, View(dOUT) if tr else None, ctot
+                producers = [(u1, 0, 0), (u2, 0, c0), (u3, 0, c0 + c1b), (u4, 0, c0 + c1b + c2b)]
         self.tower_out, self.d_tower_out, self.tower_c, self.tower_h = act, dact, c, h
         self.feat = self.new(B, c)
         self.dfeat = self.new(B, c) if tr else None

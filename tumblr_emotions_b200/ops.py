@@ -142,9 +142,9 @@ def masked_colsum_split(dy: View, y: SView, sums, beta=None, sums_ld=0):
 
 
 def maxpool_bwd_bn_apply_split(dyp: View, argmax, z: View, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, mean, rstd, beta, sums, sums_ld,
-                               dz: SView, dbeta):
-    lib().maxpool_bwd_bn_apply_split(dyp.ptr, dyp.ld, _p(argmax), z.ptr, z.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, _p(mean),
-                                     _p(rstd), _p(beta), _p(sums), sums_ld, dz.ptr, dz.lo_ptr, dz.ld, _p(dbeta), _stream())
+                               dz: SView, dbeta, arg_off=0, arg_ld=0):
+    lib().maxpool_bwd_bn_apply_split(dyp.ptr, dyp.ld, _p(argmax) + arg_off, z.ptr, z.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, _p(mean),
+                                     _p(rstd), _p(beta), _p(sums), sums_ld, dz.ptr, dz.lo_ptr, dz.ld, _p(dbeta), arg_ld, _stream())
 
 
 def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SView = None, dgrad_tap: int = None, fwd_rs: int = 0):
@@ -181,10 +181,10 @@ def maxpool_fwd_split(x: SView, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo,
 
 def maxpool_bn_relu_split(z: View, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, beta, y: SView, eps, flags=0, mean=None, rstd=None,
                           stats=None, stats_ld=0, mean_out=None, rstd_out=None, moving_mean=None, moving_var=None, momentum=0.0,
-                          argmax=None):
+                          argmax=None, arg_off=0, arg_ld=0):
     lib().maxpool_bn_relu_split(z.ptr, z.ld, batch, h, w, c, k, stride, pad_t, pad_l, ho, wo, _p(mean), _p(rstd), eps, _p(beta), flags,
                                 _p(stats), stats_ld, _p(mean_out), _p(rstd_out), _p(moving_mean), _p(moving_var), momentum, y.ptr,
-                                y.lo_ptr, y.ld, _p(argmax), _stream())
+                                y.lo_ptr, y.ld, (_p(argmax) + arg_off) if argmax is not None else 0, arg_ld, _stream())
 
 
 def avgpool_dropout_fwd_split(x: SView, batch, hw, c, mask, inv_keep, out: View):
