@@ -5,6 +5,7 @@
 // weight repack.  Reference sites: slim.batch_norm via slim/nets/inception_utils.py:48-70, slim.max_pool2d /
 // avg_pool2d image_model/inception_v1.py:67,79,94,118,208,299.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -245,63 +246,91 @@ __global__ void bn_dbeta_kernel(const double* __restrict__ sums, int n, float* _
 }
 
 // ---- pooling on split activations ----------------------------------------------------------------------------------
-// 8 channels per thread (16-byte loads per plane); the K x K window is fully unrolled with clamped coordinates and validity
-// predicates so that all 2*K*K loads are in flight together.  First maximum in scan order wins (TF MaxPool / MaxPoolGrad).
-template <int K>
-__global__ void __launch_bounds__(256) maxpool_fwd_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
-                                                                int64_t ldx, int64_t B, int h, int w, int c8, int stride,
-                                                                int pad_t, int pad_l, int ho, int wo, uint16_t* __restrict__ y_hi,
-                                                                uint16_t* __restrict__ y_lo, int64_t ldy,
-                                                                uint8_t* __restrict__ argmax) {
-  // one CTA per output row (b, p): a single 32-bit division per work item instead of a div/mod chain
+// Max pool on split activations, SIMD over channel pairs: the value order of x = hi + lo is the lexicographic order of (hi, lo)
+// (hi = bf16(x) is monotone in x, and for equal hi the larger lo is the larger x), so the window maximum is found without ever
+// merging the planes - per tap and per PAIR of channels: one packed bf16 max over the hi words, one packed equality mask, one
+// packed max over the lo words of the taps that tie on hi, one more equality mask and a bitwise select that records the first
+// winning tap (TF scan order).  The winning hi / lo words are stored as they are.  One CTA per output row, 8 channels per thread.
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+// QW consecutive outputs along w share their loads (stride 1: 3 x (QW + 2) taps instead of QW x 9).
+template <int K, int QW>
+__global__ void __launch_bounds__(128) maxpool_fwd_split_simd_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
+                                                                     int64_t ldx, int64_t B, int h, int w, int c8, int stride, int pad_t,
+                                                                     int pad_l, int ho, int wo, uint16_t* __restrict__ y_hi,
+                                                                     uint16_t* __restrict__ y_lo, int64_t ldy,
+                                                                     uint8_t* __restrict__ argmax) {
+  constexpr uint32_t NEG_INF2 = 0xFF80FF80u;            // packed bf16 -inf: never wins, never ties
+  constexpr int KW = K + QW - 1;                         // taps along w loaded per thread (QW > 1 only with stride 1)
   const int64_t b = blockIdx.x / (uint32_t)ho;
   const int p = (int)(blockIdx.x - b * ho);
-  const uint32_t row_items = (uint32_t)wo * (uint32_t)c8;
+  const int wq = (wo + QW - 1) / QW;
+  const uint32_t row_items = (uint32_t)wq * (uint32_t)c8;
   for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
-    const int q = (int)(i / (uint32_t)c8);
-    const int cg = (int)(i - (uint32_t)q * (uint32_t)c8);
-    const int ih0 = p * stride - pad_t, iw0 = q * stride - pad_l;
-    uint4 hv[K * K], lv[K * K];
-    bool ok[K * K];
+    const int q0 = (int)(i / (uint32_t)c8) * QW;
+    const int cg = (int)(i % (uint32_t)c8);
+    const int ih0 = p * stride - pad_t, iw0 = q0 * stride - pad_l;
+    uint4 hv[K * KW], lv[K * KW];
 #pragma unroll
     for (int r = 0; r < K; ++r)
 #pragma unroll
-      for (int s = 0; s < K; ++s) {
-        const int ih = ih0 + r, iw = iw0 + s;
-        const bool v = ih >= 0 && ih < h && iw >= 0 && iw < w;
-        ok[r * K + s] = v;
-        const int64_t off = ((b * h + (v ? ih : 0)) * (int64_t)w + (v ? iw : 0)) * ldx + cg * 8;
-        hv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
-        lv[r * K + s] = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+      for (int sx = 0; sx < KW; ++sx) {
+        const int ih = ih0 + r, iw = iw0 + sx;
+        const bool ok = ih >= 0 && ih < h && iw >= 0 && iw < w;
+        hv[r * KW + sx] = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2);
+        lv[r * KW + sx] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+          const int64_t off = ((b * h + ih) * (int64_t)w + iw) * ldx + cg * 8;
+          hv[r * KW + sx] = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
+          lv[r * KW + sx] = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+        }
       }
-    // per element: one 32-bit word (hi << 16 | lo) travels with the running maximum; value = float(hi) + float(lo)
-    float best[8];
-    uint32_t bw[8], arg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bw[j] = 0; arg[j] = 255; }
+    for (int j = 0; j < QW; ++j) {
+      const int q = q0 + j;
+      if (q >= wo) break;
+      uint32_t oh[4], ol[4], pos[4];
 #pragma unroll
-    for (int tp = 0; tp < K * K; ++tp) {
-      if (!ok[tp]) continue;
-      const uint32_t hw[4] = {hv[tp].x, hv[tp].y, hv[tp].z, hv[tp].w}, lw[4] = {lv[tp].x, lv[tp].y, lv[tp].z, lv[tp].w};
+      for (int k = 0; k < 4; ++k) {
+        uint32_t H[K * K], L[K * K];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // bytes {lo16 of element j, hi16 of element j}: __byte_perm picks them out of the (lo word, hi word) pair
-        const uint32_t wj = __byte_perm(lw[j >> 1], hw[j >> 1], (j & 1) ? 0x7632 : 0x5410);
-        const float v = __uint_as_float(wj & 0xffff0000u) + __uint_as_float(wj << 16);
-        if (v > best[j]) { best[j] = v; bw[j] = wj; arg[j] = tp; }
+        for (int r = 0; r < K; ++r)
+#pragma unroll
+          for (int sx = 0; sx < K; ++sx) {
+            const uint4 h4 = hv[r * KW + sx + j], l4 = lv[r * KW + sx + j];
+            H[r * K + sx] = k == 0 ? h4.x : k == 1 ? h4.y : k == 2 ? h4.z : h4.w;
+            L[r * K + sx] = k == 0 ? l4.x : k == 1 ? l4.y : k == 2 ? l4.z : l4.w;
+          }
+        uint32_t M = H[0];
+#pragma unroll
+        for (int t = 1; t < K * K; ++t) M = bf2_max(M, H[t]);
+        uint32_t E[K * K], C[K * K];
+#pragma unroll
+        for (int t = 0; t < K * K; ++t) {
+          E[t] = bf2_eq_mask(H[t], M);                         // 0xffff in the halves whose hi ties with the maximum
+          C[t] = (L[t] & E[t]) | (NEG_INF2 & ~E[t]);           // lo of the candidates, -inf elsewhere
+        }
+        uint32_t ML = C[0];
+#pragma unroll
+        for (int t = 1; t < K * K; ++t) ML = bf2_max(ML, C[t]);
+        uint32_t ps = 0;
+#pragma unroll
+        for (int t = K * K - 1; t >= 0; --t) {                 // descending: the first winning tap is written last
+          const uint32_t W = bf2_eq_mask(C[t], ML) & E[t];
+          ps = (ps & ~W) | (((uint32_t)t * 0x00010001u) & W);
+        }
+        oh[k] = M; ol[k] = ML; pos[k] = ps;
       }
-    }
-    uint32_t bh[8], bl[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { bh[j] = bw[j] >> 16; bl[j] = bw[j] & 0xffffu; }
-    const int64_t o = ((b * ho + p) * (int64_t)wo + q);
-    *reinterpret_cast<uint4*>(y_hi + o * ldy + cg * 8) =
-        make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
-    *reinterpret_cast<uint4*>(y_lo + o * ldy + cg * 8) =
-        make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
-    if (argmax) {
-      *reinterpret_cast<uint2*>(argmax + (o * c8 + cg) * 8) =
-          make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24), arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24));
+      const int64_t o = ((b * ho + p) * (int64_t)wo + q);
+      *reinterpret_cast<uint4*>(y_hi + o * ldy + cg * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      *reinterpret_cast<uint4*>(y_lo + o * ldy + cg * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      if (argmax)      // bytes 0 and 2 of each pos word are the tap indices of its two channels
+        *reinterpret_cast<uint2*>(argmax + (o * c8 + cg) * 8) = make_uint2(__byte_perm(pos[0], pos[1], 0x6420), __byte_perm(pos[2], pos[3], 0x6420));
     }
   }
 }
@@ -388,91 +417,6 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
                     fmaxf((mx.z - mu[2]) * rs[2] + be.z, 0.f), fmaxf((mx.w - mu[3]) * rs[3] + be.w, 0.f)};
     const int64_t o = ((b * ho + p) * (int64_t)wo + q);
     ds::store4_split(y_hi + o * ldy + col, y_lo + o * ldy + col, out);
-  }
-}
-
-// 3x3 / stride 1 / pad 1 (the in-block pools): a thread produces a 2x2 patch of outputs for 4 channels from the 4x4 input
-// patch it loads once - 16 tap loads per 4 outputs instead of 36 (the kernel is bound by L1 bandwidth, not HBM).
-// Taps are visited in row-major order, so every output still sees its window in TF scan order (first maximum wins).
-__global__ void __launch_bounds__(128) maxpool3s1_fwd_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
-                                                                   int64_t ldx, int64_t B, int h, int w, int c4,
-                                                                   uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
-                                                                   uint8_t* __restrict__ argmax) {
-  const int ph = (h + 1) >> 1, pw = (w + 1) >> 1;
-  const int64_t b = blockIdx.x / (uint32_t)ph;
-  const int p0 = (int)(blockIdx.x - b * ph) * 2;
-  const uint32_t row_items = (uint32_t)pw * (uint32_t)c4;
-  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
-    const int pc = (int)(i / (uint32_t)c4);
-    const int cg = (int)(i - (uint32_t)pc * (uint32_t)c4);
-    const int q0 = pc * 2;
-    uint2 hv[16], lv[16];
-    bool ok[16];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int ih = p0 - 1 + a, iw = q0 - 1 + c;
-        const bool v = ih >= 0 && ih < h && iw >= 0 && iw < w;
-        ok[a * 4 + c] = v;
-        const int64_t off = ((b * h + (v ? ih : 0)) * (int64_t)w + (v ? iw : 0)) * ldx + cg * 4;
-        hv[a * 4 + c] = __ldg(reinterpret_cast<const uint2*>(x_hi + off));
-        lv[a * 4 + c] = __ldg(reinterpret_cast<const uint2*>(x_lo + off));
-      }
-    // First-wins maxima with shared sub-results: per input row a, m12 = fw(col1, col2) feeds both R[a][0] = fw(col0, m12) and
-    // R[a][1] = fw(m12, col3); vertically v12 = fw(R[1], R[2]) feeds out(dp=0) = fw(R[0], v12) and out(dp=1) = fw(v12, R[3]).
-    // fw(x, y) keeps x unless y is strictly greater, i.e. the earlier element in TF scan order wins ties.  A state is
-    // (value, packed hi|lo word, position a*4+c); invalid taps carry -inf.
-    float best[4][4];
-    uint32_t bw[4][4], arg[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float rv[4][2]; uint32_t rw[4][2], rp[4][2];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        float tv[4]; uint32_t tw[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t hwj = (j >> 1) ? hv[a * 4 + c].y : hv[a * 4 + c].x, lwj = (j >> 1) ? lv[a * 4 + c].y : lv[a * 4 + c].x;
-          tw[c] = __byte_perm(lwj, hwj, (j & 1) ? 0x7632 : 0x5410);
-          tv[c] = ok[a * 4 + c] ? __uint_as_float(tw[c] & 0xffff0000u) + __uint_as_float(tw[c] << 16) : -INFINITY;
-        }
-        const bool g12 = tv[2] > tv[1];
-        const float v12 = g12 ? tv[2] : tv[1]; const uint32_t w12 = g12 ? tw[2] : tw[1]; const uint32_t p12 = a * 4 + (g12 ? 2 : 1);
-        const bool g0 = v12 > tv[0];
-        rv[a][0] = g0 ? v12 : tv[0]; rw[a][0] = g0 ? w12 : tw[0]; rp[a][0] = g0 ? p12 : (uint32_t)(a * 4);
-        const bool g3 = tv[3] > v12;
-        rv[a][1] = g3 ? tv[3] : v12; rw[a][1] = g3 ? tw[3] : w12; rp[a][1] = g3 ? (uint32_t)(a * 4 + 3) : p12;
-      }
-#pragma unroll
-      for (int dq = 0; dq < 2; ++dq) {
-        const bool g12 = rv[2][dq] > rv[1][dq];
-        const float v12 = g12 ? rv[2][dq] : rv[1][dq]; const uint32_t w12 = g12 ? rw[2][dq] : rw[1][dq], p12 = g12 ? rp[2][dq] : rp[1][dq];
-        const bool g0 = v12 > rv[0][dq];
-        best[dq][j] = g0 ? v12 : rv[0][dq]; bw[dq][j] = g0 ? w12 : rw[0][dq];
-        const uint32_t pos0 = g0 ? p12 : rp[0][dq];
-        const bool g3 = rv[3][dq] > v12;
-        best[2 + dq][j] = g3 ? rv[3][dq] : v12; bw[2 + dq][j] = g3 ? rw[3][dq] : w12;
-        const uint32_t pos1 = g3 ? rp[3][dq] : p12;
-        // position (row a, col c) of the 4x4 patch -> tap index inside the output's own 3x3 window
-        arg[dq][j] = ((pos0 >> 2) - 0) * 3 + ((pos0 & 3) - dq);
-        arg[2 + dq][j] = ((pos1 >> 2) - 1) * 3 + ((pos1 & 3) - dq);
-      }
-    }
-#pragma unroll
-    for (int dp = 0; dp < 2; ++dp)
-#pragma unroll
-      for (int dq = 0; dq < 2; ++dq) {
-        const int p = p0 + dp, q = q0 + dq, o = dp * 2 + dq;
-        if (p >= h || q >= w) continue;
-        const int64_t oi = ((b * h + p) * (int64_t)w + q);
-        *reinterpret_cast<uint2*>(y_hi + oi * ldy + cg * 4) =
-            make_uint2((bw[o][0] >> 16) | (bw[o][1] & 0xffff0000u), (bw[o][2] >> 16) | (bw[o][3] & 0xffff0000u));
-        *reinterpret_cast<uint2*>(y_lo + oi * ldy + cg * 4) =
-            make_uint2((bw[o][0] & 0xffffu) | (bw[o][1] << 16), (bw[o][2] & 0xffffu) | (bw[o][3] << 16));
-        if (argmax)
-          *reinterpret_cast<uint32_t*>(argmax + (oi * c4 + cg) * 4) = arg[o][0] | (arg[o][1] << 8) | (arg[o][2] << 16) | (arg[o][3] << 24);
-      }
   }
 }
 
@@ -810,15 +754,13 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
   const int64_t total = batch * ho * wo * (c / 8);
   DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
-  if (k == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && ho == h && wo == w)
-    maxpool3s1_fwd_split_kernel<<<(unsigned)(batch * ((h + 1) / 2)), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 4),
-                                                                                            y_hi, y_lo, ldy, argmax);
-  else if (k == 3)
-    maxpool_fwd_split_kernel<3><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
-                                                                                pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
-  else
-    maxpool_fwd_split_kernel<2><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), stride,
-                                                                                pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax);
+#define DS_GO(KK, QQ)                                                                                                               \
+  maxpool_fwd_split_simd_kernel<KK, QQ><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), \
+      stride, pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax)
+  if (k == 3 && stride == 1) DS_GO(3, 2);
+  else if (k == 3) DS_GO(3, 1);
+  else DS_GO(2, 1);
+#undef DS_GO
   DS_LAUNCH_CHECK();
   return 0;
 }
