@@ -77,7 +77,8 @@ int ds_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint1
 int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t rows, int64_t cols, float* out, int64_t ldo,
                   void* stream);
 /* out[(tap*cin + c), m] = x[pixel(m) + tap - pad, c] (0 outside the image): the pixel-major (K-major) operands of the
- * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w. */
+ * weight-gradient GEMMs; ksize 1 is a plain transpose.  ldo >= batch*h*w; each plane row must have room for batch*h*w rounded up
+ * to a multiple of 8 pixels (the tail is zero-filled). */
 int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w,
                               int64_t cin, int ksize, uint16_t* o_hi, uint16_t* o_lo, int64_t ldo, void* stream);
 /* The 7x7/2 stem conv (image_model/inception_v1.py:63) in space-to-depth form.  ds_s2d_split: dense fp32 NHWC image [B,H,W,3] ->

@@ -447,39 +447,66 @@ __global__ void __launch_bounds__(256) avgpool_fwd_split_kernel(const uint16_t* 
 
 // ---- operand transposes for the weight-gradient GEMMs ----------------------------------------------------------------
 // out[(tap*cin + c), m] = x[pixel(m) + tap - pad, c] (0 outside the image), both planes.  ksize = 1 is a plain
-// transpose.  grid (m tiles, c tiles, taps), block (32, 8), 32x32 tiles through shared memory.
+// transpose.  grid (m tiles, c tiles, taps), 256 threads, 64 x 64 tiles through shared memory: 16-byte loads along c,
+// 16-byte stores along m (cin % 8 == 0 and 16-byte aligned rows select the vector path, anything else the scalar one).
+template <bool VEC>
 __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
                                                                      int64_t ldx, int64_t M, int h, int w, int cin, int ks, int pad,
                                                                      uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
                                                                      int64_t ldo) {
-  __shared__ uint16_t th[32][34], tl[32][34];
+  __shared__ __align__(16) uint16_t th[64][72], tl[64][72];        // [m][c], rows padded to 144 bytes
   const int tap = blockIdx.z, r = tap / ks, s = tap - r * ks;
-  const int64_t m0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t m = m0 + i;
-    const int c = c0 + threadIdx.x;
-    uint16_t vh = 0, vl = 0;
-    if (m < M && c < cin) {
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  // load: thread -> (pixel tid / 8 (+32), 8 channels (tid % 8) * 8)
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int mi = (tid >> 3) + it * 32, cj = (tid & 7) * 8;
+    const int64_t m = m0 + mi;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+    if (m < M) {
       const int q = (int)(m % w);
       const int64_t t2 = m / w;
       const int pp = (int)(t2 % h);
       const int64_t b = t2 / h;
       const int ih = pp - pad + r, iw = q - pad + s;
       if (ih >= 0 && ih < h && iw >= 0 && iw < w) {
-        const int64_t off = ((b * h + ih) * (int64_t)w + iw) * ldx + c;
-        vh = x_hi[off]; vl = x_lo[off];
+        const int64_t off = ((b * h + ih) * (int64_t)w + iw) * ldx + c0 + cj;
+        if (VEC) {
+          if (c0 + cj < cin) { vh = __ldg(reinterpret_cast<const uint4*>(x_hi + off)); vl = __ldg(reinterpret_cast<const uint4*>(x_lo + off)); }
+        } else {
+          uint16_t eh[8], el[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const bool ok = c0 + cj + e < cin; eh[e] = ok ? x_hi[off + e] : 0; el[e] = ok ? x_lo[off + e] : 0; }
+          vh = make_uint4(eh[0] | (eh[1] << 16), eh[2] | (eh[3] << 16), eh[4] | (eh[5] << 16), eh[6] | (eh[7] << 16));
+          vl = make_uint4(el[0] | (el[1] << 16), el[2] | (el[3] << 16), el[4] | (el[5] << 16), el[6] | (el[7] << 16));
+        }
       }
     }
-    th[i][threadIdx.x] = vh; tl[i][threadIdx.x] = vl;
+    *reinterpret_cast<uint4*>(&th[mi][cj]) = vh;
+    *reinterpret_cast<uint4*>(&tl[mi][cj]) = vl;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i;
-    const int64_t m = m0 + threadIdx.x;
+  // store: thread -> (channel tid / 8 (+32), 8 pixels (tid % 8) * 8)
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int ci = (tid >> 3) + it * 32, mj = (tid & 7) * 8;
+    const int c = c0 + ci;
+    const int64_t m = m0 + mj;
     if (c < cin && m < M) {
+      uint16_t eh[8], el[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { eh[e] = th[mj + e][ci]; el[e] = tl[mj + e][ci]; }
       const int64_t off = ((int64_t)tap * cin + c) * ldo + m;
-      o_hi[off] = th[threadIdx.x][i]; o_lo[off] = tl[threadIdx.x][i];
+      if (VEC) {      // rows are padded to a multiple of 8 pixels: the tail group stores zeros into the padding
+        *reinterpret_cast<uint4*>(o_hi + off) = make_uint4(eh[0] | (eh[1] << 16), eh[2] | (eh[3] << 16), eh[4] | (eh[5] << 16), eh[6] | (eh[7] << 16));
+        *reinterpret_cast<uint4*>(o_lo + off) = make_uint4(el[0] | (el[1] << 16), el[2] | (el[3] << 16), el[4] | (el[5] << 16), el[6] | (el[7] << 16));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (m + e < M) { o_hi[off + e] = eh[e]; o_lo[off + e] = el[e]; }
+      }
     }
   }
 }
@@ -802,9 +829,15 @@ int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_
   const int64_t M = batch * h * w;
   DS_REQUIRE(ldo >= M, "output row stride too small");
   if (M == 0 || cin == 0) return 0;
-  dim3 grid((unsigned)ds::cdiv(M, 32), (unsigned)ds::cdiv(cin, 32), (unsigned)(ksize * ksize));
-  im2col_transpose_split_kernel<<<grid, dim3(32, 8), 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize,
-                                                                       (ksize - 1) / 2, o_hi, o_lo, ldo);
+  dim3 grid((unsigned)ds::cdiv(M, 64), (unsigned)ds::cdiv(cin, 64), (unsigned)(ksize * ksize));
+  const bool vec = cin % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 &&
+                   (((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)o_hi | (uintptr_t)o_lo) & 15) == 0;
+  if (vec)
+    im2col_transpose_split_kernel<true><<<grid, 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
+                                                                        o_hi, o_lo, ldo);
+  else
+    im2col_transpose_split_kernel<false><<<grid, 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
+                                                                         o_hi, o_lo, ldo);
   DS_LAUNCH_CHECK();
   return 0;
 }
