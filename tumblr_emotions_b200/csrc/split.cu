@@ -606,15 +606,30 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
                                                                          uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo,
                                                                          int64_t lddz, float* dbeta, int64_t arg_ld) {
   constexpr int NW = (K + S - 1) / S;
-  const int64_t b = blockIdx.x / (uint32_t)h;
-  const int ih = (int)(blockIdx.x - b * h);
+  // column-fixed threads: blockDim = (channel groups, pixel lanes); a thread keeps its 4 channels' parameters in registers
+  const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= c4) return;
+  const int col = cg * 4;
+  const int64_t b = blockIdx.y / (uint32_t)h;
+  const int ih = (int)(blockIdx.y - b * h);
   const double inv_m = 1.0 / ((double)B * h * w);
-  const uint32_t row_items = (uint32_t)w * (uint32_t)c4;
-  for (uint32_t i = threadIdx.x; i < row_items; i += blockDim.x) {
-    const int iw = (int)(i / (uint32_t)c4);
-    const int cg = (int)(i - (uint32_t)iw * (uint32_t)c4);
-    const int col = cg * 4;
-    const int p_hi = (ih + pad_t) / S, q_hi = (iw + pad_l) / S;
+  const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+  const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m1[j] = (float)(sums[col + j] * inv_m);
+    m2[j] = (float)(sums[sums_ld + col + j] * inv_m);
+  }
+  if (dbeta && blockIdx.y == 0 && threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dbeta[col + j] = (float)sums[col + j];
+  }
+  const int p_hi = (ih + pad_t) / S;
+  for (int iw = threadIdx.y; iw < w; iw += blockDim.y) {
+    const int q_hi = (iw + pad_l) / S;
     const int64_t pix = (b * h + ih) * (int64_t)w + iw;
     const float4 zv = __ldg(reinterpret_cast<const float4*>(z + pix * ldz + col));
     uint32_t mk[NW * NW];
@@ -643,24 +658,15 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
         g[3] += (mk[n] & 0xff000000u) ? gv.w : 0.f;
       }
     }
-    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
-    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
-    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
     const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
     float out[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float xh = (zz[j] - mu[j]) * rs[j];
       const float gm = (xh + be[j] > 0.f) ? g[j] : 0.f;
-      const float m1 = (float)(sums[col + j] * inv_m), m2 = (float)(sums[sums_ld + col + j] * inv_m);
-      out[j] = rs[j] * (gm - m1 - xh * m2);
+      out[j] = rs[j] * (gm - m1[j] - xh * m2[j]);
     }
     ds::store4_split(dz_hi + pix * lddz + col, dz_lo + pix * lddz + col, out);
-    if (dbeta && blockIdx.x == 0 && iw == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dbeta[col + j] = (float)sums[col + j];
-    }
   }
 }
 
@@ -875,9 +881,13 @@ int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t*
   DS_REQUIRE(c % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0 && lddz % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dyp) & 15) == 0, "16-byte alignment");
   if (batch * h * w * c == 0) return 0;
-  const unsigned blocks = (unsigned)(batch * h);
+  const int c4 = (int)(c / 4);
+  int cgs = std::min(c4, 64);
+  while (c4 % cgs != 0 && cgs > 16) --cgs;                // widest x-extent <= 64 that divides the channel groups (or 16)
+  const dim3 blk(cgs, std::max(1, 256 / cgs));
+  const dim3 blocks((unsigned)ds::cdiv(c4, cgs), (unsigned)(batch * h));
 #define DS_GO(KK, SS)                                                                                                              \
-  maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, 256, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
+  maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, blk, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
       (int)(c / 4), pad_t, pad_l, (int)ho, (int)wo, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta, arg_ld > 0 ? arg_ld : c)
   if (k == 3 && stride == 2) DS_GO(3, 2);
   else if (k == 2 && stride == 2) DS_GO(2, 2);
