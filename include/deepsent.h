@@ -229,7 +229,8 @@ int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const
                       const int64_t* seq_len, int64_t t, int64_t batch, int64_t n, float forget_bias,
                       float* gates, float* c_out, float* h_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ldh, void* stream);
 /* BPTT step: dh = dh_rec + dh_carry, dc in/out; writes dz [batch,4n] (+ optional split-bf16 copy); updates carries.
- * dh_rec (optional) is consumed and left ZEROED, ready for the split-K recurrent contraction that accumulates into it. */
+ * dh_rec (optional) is consumed and left ZEROED, ready for the split-K recurrent contraction that accumulates into it.
+ * Either of dz (fp32) and dz_hi/dz_lo (split) may be NULL. */
 int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cur, const int64_t* seq_len,
                       int64_t t, int64_t batch, int64_t n, float* dh_rec, float* dh_carry, float* dc,
                       float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream);

@@ -103,10 +103,12 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
     if (!live) {   // state was carried: gradient passes through untouched, no gate gradient
       *reinterpret_cast<float4*>(dh_carry + sb) = make_float4(dh[0], dh[1], dh[2], dh[3]);
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(dz + gbase) = zero;
-      *reinterpret_cast<float4*>(dz + gbase + n) = zero;
-      *reinterpret_cast<float4*>(dz + gbase + 2 * n) = zero;
-      *reinterpret_cast<float4*>(dz + gbase + 3 * n) = zero;
+      if (dz) {
+        *reinterpret_cast<float4*>(dz + gbase) = zero;
+        *reinterpret_cast<float4*>(dz + gbase + n) = zero;
+        *reinterpret_cast<float4*>(dz + gbase + 2 * n) = zero;
+        *reinterpret_cast<float4*>(dz + gbase + 3 * n) = zero;
+      }
       if (dz_hi) {
         const float z4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -135,10 +137,12 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
       df[k] = dct * cp[k] * gf[k] * (1.f - gf[k]);
       dcp[k] = dct * gf[k];
     }
-    *reinterpret_cast<float4*>(dz + gbase) = make_float4(di[0], di[1], di[2], di[3]);
-    *reinterpret_cast<float4*>(dz + gbase + n) = make_float4(dj[0], dj[1], dj[2], dj[3]);
-    *reinterpret_cast<float4*>(dz + gbase + 2 * n) = make_float4(df[0], df[1], df[2], df[3]);
-    *reinterpret_cast<float4*>(dz + gbase + 3 * n) = make_float4(dob[0], dob[1], dob[2], dob[3]);
+    if (dz) {
+      *reinterpret_cast<float4*>(dz + gbase) = make_float4(di[0], di[1], di[2], di[3]);
+      *reinterpret_cast<float4*>(dz + gbase + n) = make_float4(dj[0], dj[1], dj[2], dj[3]);
+      *reinterpret_cast<float4*>(dz + gbase + 2 * n) = make_float4(df[0], df[1], df[2], df[3]);
+      *reinterpret_cast<float4*>(dz + gbase + 3 * n) = make_float4(dob[0], dob[1], dob[2], dob[3]);
+    }
     if (dz_hi) {
       ds::store4_split(dz_hi + b * lddz + u, dz_lo + b * lddz + u, di);
       ds::store4_split(dz_hi + b * lddz + n + u, dz_lo + b * lddz + n + u, dj);

@@ -620,14 +620,18 @@ class Engine:
             self.whT, self.wh, self.wxT = SView(self.new_split((4 * n,), n)), SView(self.new_split((n,), 4 * n)), \
                 SView(self.new_split((4 * n,), EMB_LD))
         if tr:
-            self.DZ = self.new(T * B, 4 * n)
             self.dh_carry, self.dc, self.dh_rec = self.new(B, n), self.new(B, n), self.new(B, n)
             if self.split:
                 ld = (T * B + 7) // 8 * 8
                 self.DZs = self.new_split((T, B), 4 * n)
-                self.HsT = SView(self.new_split((n,), ld))                   # pixel... time-major operands of the weight gradients
+                self.HsT = SView(self.new_split((n,), ld))                   # time-major (K-major) operands of the weight gradients
                 self.DZsT = SView(self.new_split((4 * n,), ld))
-                self.EsT = SView(self.new_split((self.emb_dim,), ld))
+                # [E^T ; 1]: the extra row of ones makes the same GEMM produce the bias gradient (column sums of dZ)
+                self.EsT = SView(self.new_split((self.emb_dim + 1,), ld))
+                self.EsT.base.view(self.emb_dim + 1, 2 * ld)[self.emb_dim, :T * B] = 1.0
+                self._dke = self.new(self.emb_dim + 1, 4 * n)
+            else:
+                self.DZ = self.new(T * B, 4 * n)
 
     def text_fwd(self, train: bool):
         B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
@@ -659,7 +663,7 @@ class Engine:
         for t in reversed(range(T)):
             dzs = SView(self.DZs[t]) if self.split else None
             ops.lstm_gates_bwd(self.G[t], self.C[t], self.C[t + 1], self.seq_lens, t, B, n, self.dh_rec if t < T - 1 else None,
-                               self.dh_carry, self.dc, self.DZ[t * B:(t + 1) * B], dzs)
+                               self.dh_carry, self.dc, None if self.split else self.DZ[t * B:(t + 1) * B], dzs)
             if t > 0:
                 if self.split:      # K = 4n is long and M x N small: split-K keeps all SMs busy with 8x less operand traffic
                     ops.gemm_bf16x3(dzs, self.wh, View(self.dh_rec), ksplit=8)      # dh_rec was left zeroed by lstm_gates_bwd
@@ -671,17 +675,20 @@ class Engine:
             TB = T * B
             ops.im2col_transpose_split(SView(self.DZs), TB, 1, 1, 4 * n, 1, self.DZsT)
             ops.im2col_transpose_split(SView(self.Hs[:T]), TB, 1, 1, n, 1, self.HsT)
-            ops.im2col_transpose_split(self.Es, TB, 1, 1, e, 1, self.EsT)
+            ops.im2col_transpose_split(self.Es, TB, 1, 1, e, 1, self.EsT.rows_slice(0, e))
             dk.zero_()
+            self._dke.zero_()
             chunks = -(-TB // 64)
             ks = max(1, min(chunks, -(-2 * self.sm_count // (-(-n // 128) * -(-4 * n // 256)))))
             ops.gemm_bf16x3(self.HsT, self.DZsT, View(dk[e:]), k=TB, ksplit=ks)
             ks = max(1, min(chunks, -(-2 * self.sm_count // -(-4 * n // 256))))
-            ops.gemm_bf16x3(self.EsT, self.DZsT, View(dk[:e]), k=TB, ksplit=ks)
+            ops.gemm_bf16x3(self.EsT, self.DZsT, View(self._dke), k=TB, ksplit=ks)
+            ops.copy2d(View(self._dke[:e]), View(dk[:e]))
+            ops.copy2d(View(self._dke[e:]), View(self.grad("Text/rnn/basic_lstm_cell/bias").view(1, 4 * n)))
         else:
             ops.gemm_tn(View(self.E, e), View(self.DZ), View(dk[:e]))
             ops.gemm_tn(View(self.H[:T].view(T * B, n)), View(self.DZ), View(dk[e:]))
-        ops.colsum(View(self.DZ), self.grad("Text/rnn/basic_lstm_cell/bias"))
+            ops.colsum(View(self.DZ), self.grad("Text/rnn/basic_lstm_cell/bias"))
 
     # -- head ------------------------------------------------------------------------------------------------
     def _build_head(self):
@@ -831,7 +838,7 @@ class Engine:
     # -- CUDA graph ----------------------------------------------------------------------------------------
     def capture(self, allreduce=None):
         """Capture the step into CUDA graphs (one when single-GPU; fwd+bwd | update around the all-reduce otherwise)."""
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(priority=-1)      # image tower (critical path) above the side stream's text tower
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self.fwd_bwd()                      # warm-up outside capture (lazy module loading, attribute setting)
@@ -840,7 +847,7 @@ class Engine:
         from ._lib import lib
         n0 = lib().debug_get(15)
         self._g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g1):
+        with torch.cuda.graph(self._g1, stream=s):
             self.fwd_bwd()
             if allreduce is None:
                 self.apply_gradients()
