@@ -41,12 +41,36 @@ def parse():
 
 
 def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) when present, else the fallback of B200_PROFILING.md.  The
+    file's key names are matched loosely (hbm* -> GB/s, *bf16*sustain* / *bf16* -> TFLOP/s)."""
+    fb = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            p = json.load(f)
-        return p, "measured"
+            raw = json.load(f)
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+        return fb, "fallback"
+
+    def flat(d, prefix=""):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                yield from flat(v, prefix + k + ".")
+            elif isinstance(v, (int, float)):
+                yield (prefix + k).lower(), float(v)
+
+    vals = dict(flat(raw))
+    out = dict(fb)
+    hbm = [v for k, v in vals.items() if "hbm" in k and v > 100]
+    sus = [v for k, v in vals.items() if "bf16" in k and "sustain" in k]
+    burst = [v for k, v in vals.items() if "bf16" in k and "sustain" not in k and v > 10]
+    if hbm:
+        out["hbm_gbs"] = hbm[0] * (1000.0 if hbm[0] < 100 else 1.0)
+    if burst:
+        out["bf16_tflops"] = burst[0]
+    if sus:
+        out["bf16_tflops_sustained"] = sus[0]
+    elif burst:
+        out["bf16_tflops_sustained"] = burst[0]
+    return out, "measured" if (hbm or sus or burst) else "fallback"
 
 
 def conv_traffic():
