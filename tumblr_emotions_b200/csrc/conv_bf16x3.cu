@@ -60,6 +60,8 @@ struct Params {
   int row_mode;      // 1: space-to-depth stem - one tile per output image row, A = overlapping 4-pixel windows (ds_conv_s2d_rows)
   int tile_rows;     // valid rows per tile: 128, or the output width in row mode
   int rows_per_img;  // row mode: output rows per image
+  int band_rows;     // row mode: consecutive output rows handled as one work item (p.tiles counts bands); the 4 input rows of
+                     // an output row overlap with its neighbours', so a band loads band_rows + 3 rows instead of 4 * band_rows
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t& m0, int& n0, int& it0, int& it1) {
@@ -80,7 +82,8 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-  const uint32_t stage_bytes = ROW_MODE ? 2u * A_TILE_BYTES : 2u * A_TILE_BYTES + 2u * b_tile_bytes;   // row mode: B is resident
+  const uint32_t a_plane = ROW_MODE ? (uint32_t)p.tile_rows * 128u : (uint32_t)A_TILE_BYTES;       // bytes of one A plane in a ring slot
+  const uint32_t stage_bytes = ROW_MODE ? 2u * a_plane : 2u * A_TILE_BYTES + 2u * b_tile_bytes;   // row mode: B is resident
   const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;   // epilogue staging tiles (1024-aligned, 16 KB each)
   // row mode keeps the whole (small) weight operand resident: 4 K chunks x {hi, lo} x bn rows, fetched once per CTA
   const uint32_t bres = stg0 + (uint32_t)p.nstg * STG_BYTES;
@@ -133,7 +136,27 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           tma_load_2d(&tmBl, bres_bar, bres + (2 * c + 1) * b_tile_bytes, c * KC, 0);
         }
       }
-      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      if (ROW_MODE) {
+        // space-to-depth stem: a band of consecutive output rows of one image; input row j of the band is loaded once and
+        // serves the (up to) 4 output rows whose 4-row windows contain it
+        const int bands_per_img = (p.rows_per_img + p.band_rows - 1) / p.band_rows;
+        for (int64_t band = blockIdx.x; band < p.tiles; band += gridDim.x) {
+          const int bimg = (int)(band / bands_per_img);
+          const int p0 = (int)(band - (int64_t)bimg * bands_per_img) * p.band_rows;
+          const int nrows = min(p.band_rows, p.rows_per_img - p0);
+          for (int j = 0; j < nrows + 3; ++j) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t fb = full0 + 8 * s;
+            mbar_expect_tx(fb, stage_bytes);
+            const uint32_t sa = base + s * stage_bytes;
+            // box {64 = 4 pixels x 16 channels, W_out windows one pixel apart}; rows outside the image are zero-filled
+            tma_load_4d(&tmAh, fb, sa, 0, 0, p0 - 1 + j, bimg);
+            tma_load_4d(&tmAl, fb, sa + a_plane, 0, 0, p0 - 1 + j, bimg);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+      for (int64_t t = blockIdx.x; !ROW_MODE && t < p.tiles; t += gridDim.x) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
         int img = 0, hp = 0, wq = 0;
@@ -149,28 +172,19 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         for (int it = it0; it < it1; ++it) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, ROW_MODE ? 2u * (uint32_t)p.tile_rows * 128u : stage_bytes);
+          mbar_expect_tx(fb, stage_bytes);
           const int c0 = cc * KC;
           const uint32_t sa = base + s * stage_bytes;
-          if (ROW_MODE) {
-            // output row (img, prow): filter-row group `it` reads space-to-depth row prow - 1 + it (zero outside the image);
-            // the box is {64 = 4 pixels x 16 channels, W_out windows one pixel apart}
-            const int tile = (int)(m0 / p.tile_rows);
-            const int bimg = tile / p.rows_per_img, prow = tile - bimg * p.rows_per_img;
-            tma_load_4d(&tmAh, fb, sa, 0, 0, prow - 1 + it, bimg);
-            tma_load_4d(&tmAl, fb, sa + A_TILE_BYTES, 0, 0, prow - 1 + it, bimg);
-          } else if (p.ksize == 1) {
+          if (p.ksize == 1) {
             tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
             tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
           } else {
             tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
             tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
           }
-          if (!ROW_MODE) {
-            const int kb = tap * p.cin + c0;
-            tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
-            tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
-          }
+          const int kb = tap * p.cin + c0;
+          tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
+          tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
           if (++cc == p.cpt) { cc = 0; ++tap; if (++sx == p.ksize) { sx = 0; ++r; } }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -183,8 +197,46 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       uint32_t acc_it = 0;
       int s = 0; uint32_t ph = 0;
       const int nk_full = KC >> 4, nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;      // 16-channel steps per chunk
-      if (ROW_MODE) { mbar_wait(bres_bar, 0); tc_fence_after(); }
-      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
+      if (ROW_MODE) {
+        mbar_wait(bres_bar, 0);
+        tc_fence_after();
+        const int bands_per_img = (p.rows_per_img + p.band_rows - 1) / p.band_rows;
+        for (int64_t band = blockIdx.x; band < p.tiles; band += gridDim.x) {
+          const int bimg = (int)(band / bands_per_img);
+          const int p0 = (int)(band - (int64_t)bimg * bands_per_img) * p.band_rows;
+          const int nrows = min(p.band_rows, p.rows_per_img - p0);
+          // (s, ph) = ring slot / phase of the band's input row i; rows i .. i+3 feed output row i
+          for (int i = 0; i < nrows; ++i, ++acc_it) {
+            const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+            mbar_wait(tempty0 + 8 * buf, aph ^ 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * ACC_COLS;
+            int sr = s; uint32_t phr = ph;
+            for (int rr = 0; rr < 4; ++rr) {
+              mbar_wait(full0 + 8 * sr, phr);      // rows loaded for an earlier output row have completed already: returns at once
+              tc_fence_after();
+              const uint32_t ah = base + sr * stage_bytes, al = ah + a_plane;
+              const uint32_t bh = bres + (uint32_t)(2 * rr) * b_tile_bytes, bl = bh + b_tile_bytes;
+              for (int k = 0; k < (KC >> 4); ++k) {
+                const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
+                const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
+                mma_f16(acc, dal, dbh, idesc, (rr > 0 || k > 0) ? 1u : 0u);
+                mma_f16(acc, dah, dbl, idesc, 1u);
+                mma_f16(acc, dah, dbh, idesc, 1u);
+              }
+              if (++sr == p.stages) { sr = 0; phr ^= 1u; }
+            }
+            mma_commit(empty0 + 8 * s);            // input row i is not needed by later output rows
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+            mma_commit(tfull0 + 8 * buf);
+          }
+          for (int j = 0; j < 3; ++j) {            // the three trailing input rows of the band
+            mma_commit(empty0 + 8 * s);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+      for (int64_t t = blockIdx.x; !ROW_MODE && t < p.tiles; t += gridDim.x, ++acc_it) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -197,8 +249,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           tc_fence_after();
           const int nk = (cc == p.cpt - 1) ? nk_last : nk_full;
           if (++cc == p.cpt) cc = 0;
-          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES;
-          const uint32_t bh = ROW_MODE ? bres + (uint32_t)(2 * it) * b_tile_bytes : al + A_TILE_BYTES, bl = bh + b_tile_bytes;
+          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES, bh = al + A_TILE_BYTES, bl = bh + b_tile_bytes;
           for (int k = 0; k < nk; ++k) {
             const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
@@ -223,9 +274,20 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     for (int i = 0; i < ACC_COLS / 32; ++i) { s1acc[i] = 0.0; s2acc[i] = 0.0; }
     uint32_t acc_it = 0, chunk_it = 0;
     int n0_cta = 0;
-    for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
+    const int bands_per_img = ROW_MODE ? (p.rows_per_img + p.band_rows - 1) / p.band_rows : 1;
+    int row_i = 0;                                      // row mode: output row within the current band
+    for (int64_t t = blockIdx.x; t < p.tiles; ++acc_it) {
       int64_t m0; int n0, it0, it1;
-      tile_coords(p, t, m0, n0, it0, it1);
+      int band_nrows = 1;
+      if (ROW_MODE) {
+        const int bimg = (int)(t / bands_per_img);
+        const int p0 = (int)(t - (int64_t)bimg * bands_per_img) * p.band_rows;
+        band_nrows = min(p.band_rows, p.rows_per_img - p0);
+        m0 = ((int64_t)bimg * p.rows_per_img + p0 + row_i) * p.tile_rows;
+        n0 = 0; it0 = 0; it1 = 4;
+      } else {
+        tile_coords(p, t, m0, n0, it0, it1);
+      }
       n0_cta = n0;
       const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
       mbar_wait(tfull0 + 8 * buf, aph);
@@ -286,6 +348,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (++row_i == band_nrows) { row_i = 0; t += gridDim.x; }      // next work item (row mode: next band after its last row)
     }
     if (do_stats) {
       // 4 warps x 32 rows -> one value per column (shared fp64 atomics, once per CTA), then one global atomic per column
@@ -352,7 +415,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   DS_REQUIRE(p.bn % 32 == 0 && p.bn >= 32 && p.bn <= 256, "column tile must be a multiple of 32 in [32, 256]");
   p.tiles = ds::cdiv(M, BM) * p.tiles_n * p.ksplit;
   p.h = (int)h; p.w = (int)w; p.pad = (ksize - 1) / 2;
-  p.row_mode = 0; p.tile_rows = BM; p.rows_per_img = 0;
+  p.row_mode = 0; p.tile_rows = BM; p.rows_per_img = 0; p.band_rows = 0;
   const int64_t ktot = (int64_t)ksize * ksize * cin;
 
   CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
@@ -418,9 +481,11 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   p.bn = (int)((n + 31) / 32 * 32);
   p.tiles_n = 1; p.ksplit = 1;
   p.ksize = 1; p.cin = KC; p.cpt = 1; p.iters = 4; p.ipz = 4;
-  p.tiles = batch * rows;
   p.h = 0; p.w = 0; p.pad = 0;
   p.row_mode = 1; p.tile_rows = (int)wout; p.rows_per_img = (int)rows;
+  p.band_rows = (int)std::min<int64_t>(rows, 16);
+  if (ds::g_debug[7] > 0) p.band_rows = (int)std::min<int64_t>(rows, ds::g_debug[7]);
+  p.tiles = batch * ds::cdiv(rows, p.band_rows);          // work items are bands of consecutive output rows
 
   CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
   int r = 0;
@@ -442,13 +507,13 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, (uint32_t)wout, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d", r);
 
-  const int stage_bytes = 2 * A_TILE_BYTES;                       // ring slots hold only the activation planes
+  const int stage_bytes = 2 * (int)wout * 128;                    // a ring slot holds the two planes of one input row
   const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);
   const int resident_b = 8 * p.bn * 128;
-  p.nstg = 2;
+  p.nstg = 1;
   int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES - resident_b) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  DS_REQUIRE(stages >= 2, "shared-memory budget exceeded");
+  DS_REQUIRE(stages >= 4, "shared-memory budget exceeded: an output row needs its 4 input rows resident");
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + resident_b + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;
