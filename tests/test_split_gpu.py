@@ -237,7 +237,7 @@ def test_avgpool_split(K):
     close(out, ref, 1e-6, "avgpool split")
 
 
-@pytest.mark.parametrize("b,hw,n", [(2, 32, 64), (3, 64, 64), (1, 224, 64), (2, 16, 24)])
+@pytest.mark.parametrize("b,hw,n", [(2, 32, 64), (3, 64, 64), (1, 224, 64), (2, 16, 24), (2, 48, 32), (5, 80, 64)])
 def test_stem_conv_space_to_depth_matches_oracle(K, b, hw, n):
     """7x7 / stride 2 / TF-SAME (2,3) conv via ds_s2d_split + ds_conv_s2d_rows against the oracle's conv2d"""
     g = gen(13)

@@ -108,6 +108,60 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   }
 }
 
+// 3x3 / stride 1 / pad 1 (the Inception branch-3 pool): a thread owns one (image, column, 4-channel group) and walks down the
+// rows.  Window row p feeds input rows p-1, p, p+1 (tap rows 0, 1, 2), so three rolling accumulators replace the 9-window
+// gather: every argmax word and dy vector is loaded 3 times (once per horizontal neighbour) instead of 9.
+__device__ __forceinline__ void sel_add(float4& a, uint32_t m, const float4& g) {
+  a.x += (m & 0x000000ffu) ? g.x : 0.f;
+  a.y += (m & 0x0000ff00u) ? g.y : 0.f;
+  a.z += (m & 0x00ff0000u) ? g.z : 0.f;
+  a.w += (m & 0xff000000u) ? g.w : 0.f;
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_k3s1_walk_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                                    const uint8_t* __restrict__ argmax, int64_t total, int h, int w,
+                                                                    int c4, int hseg, int nseg, float* __restrict__ dx, int64_t lddx,
+                                                                    int accumulate) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c4);
+  int64_t t = idx / c4;
+  const int iw = (int)(t % w);
+  t /= w;
+  const int seg = (int)(t % nseg);
+  const int64_t b = t / nseg;
+  const int h0 = seg * hseg, h1 = min(h, h0 + hseg);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;      // input rows p-1, p, p+1
+  const bool vl = iw > 0, vr = iw + 1 < w;
+  for (int p = h0 - 1; p <= h1; ++p) {
+    const bool out_row = p - 1 >= h0;                                   // input row p-1 is complete after window row p
+    float* dst = dx + ((b * h + (p - 1)) * (int64_t)w + iw) * lddx + cg * 4;
+    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_row && accumulate) prev = *reinterpret_cast<const float4*>(dst);
+    if (p >= 0 && p < h) {
+      const int64_t o = (b * h + p) * (int64_t)w + iw;                  // pooled pixel (p, iw); its neighbours are o -+ 1
+      const uint8_t* am = argmax + (o * c4 + cg) * 4;
+      const float* g = dy + o * lddy + cg * 4;
+      // window column q = iw + dq holds this pixel at tap column s = 1 - dq
+      const uint32_t wl = vl ? __ldg(reinterpret_cast<const uint32_t*>(am - (int64_t)c4 * 4)) : 0xfefefefeu;
+      const uint32_t wc = __ldg(reinterpret_cast<const uint32_t*>(am));
+      const uint32_t wr = vr ? __ldg(reinterpret_cast<const uint32_t*>(am + (int64_t)c4 * 4)) : 0xfefefefeu;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gl = vl ? __ldg(reinterpret_cast<const float4*>(g - lddy)) : z;
+      const float4 gc = __ldg(reinterpret_cast<const float4*>(g));
+      const float4 gr = vr ? __ldg(reinterpret_cast<const float4*>(g + lddy)) : z;
+      sel_add(a0, __vcmpeq4(wl, 0x02020202u), gl); sel_add(a1, __vcmpeq4(wl, 0x05050505u), gl); sel_add(a2, __vcmpeq4(wl, 0x08080808u), gl);
+      sel_add(a0, __vcmpeq4(wc, 0x01010101u), gc); sel_add(a1, __vcmpeq4(wc, 0x04040404u), gc); sel_add(a2, __vcmpeq4(wc, 0x07070707u), gc);
+      sel_add(a0, __vcmpeq4(wr, 0x00000000u), gr); sel_add(a1, __vcmpeq4(wr, 0x03030303u), gr); sel_add(a2, __vcmpeq4(wr, 0x06060606u), gr);
+    }
+    if (out_row) {
+      prev.x += a0.x; prev.y += a0.y; prev.z += a0.z; prev.w += a0.w;
+      *reinterpret_cast<float4*>(dst) = prev;
+    }
+    a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t B, int hw, int c4,
                                                           const float* __restrict__ mask, float inv_keep,
                                                           float* __restrict__ out, int64_t ldo) {
@@ -191,6 +245,17 @@ int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t
   const int64_t total = batch * h * w * (c / 4);
   DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
+  if (k == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && ho == h && wo == w && ds::g_debug[8] != 1) {
+    // rows are walked in segments (2 halo window rows each) when whole columns would leave the GPU short of threads
+    int hseg = (int)h;
+    if (ds::g_debug[9] > 0) hseg = ds::g_debug[9];
+    const int nseg = (int)ds::cdiv(h, hseg);
+    const int64_t threads = batch * nseg * w * (c / 4);
+    maxpool_bwd_k3s1_walk_kernel<<<(unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream)>>>(dy, lddy, argmax, threads, (int)h, (int)w,
+                                                                                         (int)(c / 4), hseg, nseg, dx, lddx, accumulate);
+    DS_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (int)(batch * h);
   DS_REQUIRE(batch * h < (int64_t)1 << 31, "too many rows");
   const bool wide = c % 8 == 0;                                          // 8 channels per thread
