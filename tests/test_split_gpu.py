@@ -225,6 +225,23 @@ def test_maxpool_split_matches_fp32_kernel(K, b, h, c, k, s):
     assert torch.equal(y32.cpu(), ref)
 
 
+@pytest.mark.parametrize("b,h,c", [(2, 14, 32), (1, 28, 8), (3, 7, 832), (2, 5, 16)])
+def test_maxpool_split_stride1_ties_pick_first_tap(K, b, h, c):
+    """post-ReLU maps are full of exact zeros: the row-walking 3x3/1 kernel must record TF's first winning tap, as the fp32 kernel does"""
+    g = gen(12)
+    x = F.relu(torch.randn(b, h, h, c, generator=g))
+    x = (x * 4).round() / 4                             # few distinct values: ties between positive taps too (lo plane == 0)
+    X = to_split(K, x.view(-1, c))
+    Y = K.SView(K.new_split((b * h * h,), c, DEV))
+    arg = torch.zeros(b * h * h * c, dtype=torch.uint8, device=DEV)
+    K.maxpool_fwd_split(X, b, h, h, c, 3, 1, 1, 1, h, h, Y, arg)
+    y32 = torch.zeros(b * h * h, c, device=DEV)
+    arg32 = torch.zeros_like(arg)
+    K.maxpool_fwd(K.View(x.view(-1, c).to(DEV)), b, h, h, c, 3, 1, 1, 1, h, h, K.View(y32), arg32)
+    assert torch.equal(Y.torch(), y32)
+    assert torch.equal(arg, arg32)
+
+
 def test_avgpool_split(K):
     g = gen(12)
     b, hw, c = 3, 49, 1024

@@ -335,6 +335,91 @@ __global__ void __launch_bounds__(128) maxpool_fwd_split_simd_kernel(const uint1
   }
 }
 
+// 3x3 / stride 1 / pad 1 on split activations (the Inception branch-3 pool): a thread owns one (image, column, 8-channel group)
+// and walks down the rows.  Each input row is reduced once to its horizontal 3-tap maximum (value planes + winning tap column);
+// an output is the vertical maximum of three such rows.  First-wins ties survive the factorisation: the first row that attains
+// the window maximum, and within it the first column, is the first tap in TF's row-major scan.  3 row loads per output
+// instead of 9 (or 6 with the pairwise sharing above).
+struct PoolRow { uint32_t H[4], L[4], S[4]; };
+
+__device__ __forceinline__ void lex_max3(const uint32_t H[3], const uint32_t L[3], const uint32_t P[3], uint32_t& M, uint32_t& ML, uint32_t& ps) {
+  constexpr uint32_t NEG_INF2 = 0xFF80FF80u;
+  M = bf2_max(bf2_max(H[0], H[1]), H[2]);
+  uint32_t E[3], C[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    E[t] = bf2_eq_mask(H[t], M);
+    C[t] = (L[t] & E[t]) | (NEG_INF2 & ~E[t]);
+  }
+  ML = bf2_max(bf2_max(C[0], C[1]), C[2]);
+  ps = 0;
+#pragma unroll
+  for (int t = 2; t >= 0; --t) {                             // descending: the first winner is written last
+    const uint32_t W = bf2_eq_mask(C[t], ML) & E[t];
+    ps = (ps & ~W) | (P[t] & W);
+  }
+}
+
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+__device__ __forceinline__ PoolRow pool_row_load(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo, int64_t ldx, int64_t pix,
+                                                 int cg, bool row_ok, bool vl, bool vr) {
+  constexpr uint32_t NEG_INF2 = 0xFF80FF80u;
+  const uint4 ninf = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2), zero = make_uint4(0u, 0u, 0u, 0u);
+  uint4 hv[3] = {ninf, ninf, ninf}, lv[3] = {zero, zero, zero};
+  const int64_t off = pix * ldx + cg * 8;
+  if (row_ok) {
+    if (vl) { hv[0] = __ldg(reinterpret_cast<const uint4*>(x_hi + off - ldx)); lv[0] = __ldg(reinterpret_cast<const uint4*>(x_lo + off - ldx)); }
+    hv[1] = __ldg(reinterpret_cast<const uint4*>(x_hi + off)); lv[1] = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+    if (vr) { hv[2] = __ldg(reinterpret_cast<const uint4*>(x_hi + off + ldx)); lv[2] = __ldg(reinterpret_cast<const uint4*>(x_lo + off + ldx)); }
+  }
+  PoolRow r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t H[3] = {word_of(hv[0], k), word_of(hv[1], k), word_of(hv[2], k)};
+    const uint32_t L[3] = {word_of(lv[0], k), word_of(lv[1], k), word_of(lv[2], k)};
+    const uint32_t P[3] = {0u, 0x00010001u, 0x00020002u};
+    lex_max3(H, L, P, r.H[k], r.L[k], r.S[k]);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_split_k3s1_walk_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
+                                                                          int64_t ldx, int64_t total, int h, int w, int c8, int hseg, int nseg,
+                                                                          uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
+                                                                          uint8_t* __restrict__ argmax) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c8);
+  int64_t t = idx / c8;
+  const int iw = (int)(t % w);
+  t /= w;
+  const int seg = (int)(t % nseg);
+  const int64_t b = t / nseg;
+  const int h0 = seg * hseg, h1 = min(h, h0 + hseg);
+  const bool vl = iw > 0, vr = iw + 1 < w;
+  const int64_t col = b * h * (int64_t)w + iw;               // pixel index of (b, 0, iw)
+  PoolRow r0 = pool_row_load(x_hi, x_lo, ldx, col + (int64_t)(h0 - 1) * w, cg, h0 - 1 >= 0, vl, vr);
+  PoolRow r1 = pool_row_load(x_hi, x_lo, ldx, col + (int64_t)h0 * w, cg, true, vl, vr);
+  for (int p = h0; p < h1; ++p) {
+    const PoolRow r2 = pool_row_load(x_hi, x_lo, ldx, col + (int64_t)(p + 1) * w, cg, p + 1 < h, vl, vr);
+    uint32_t oh[4], ol[4], pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t H[3] = {r0.H[k], r1.H[k], r2.H[k]};
+      const uint32_t L[3] = {r0.L[k], r1.L[k], r2.L[k]};
+      const uint32_t P[3] = {r0.S[k], r1.S[k] + 0x00030003u, r2.S[k] + 0x00060006u};      // tap index = 3 * row + column
+      lex_max3(H, L, P, oh[k], ol[k], pos[k]);
+    }
+    const int64_t o = col + (int64_t)p * w;
+    *reinterpret_cast<uint4*>(y_hi + o * ldy + cg * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(y_lo + o * ldy + cg * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    if (argmax)
+      *reinterpret_cast<uint2*>(argmax + (o * c8 + cg) * 8) = make_uint2(__byte_perm(pos[0], pos[1], 0x6420), __byte_perm(pos[2], pos[3], 0x6420));
+    r0 = r1; r1 = r2;
+  }
+}
+
 // Fused tail of a conv whose only consumer is a max pool (the stem, image_model/inception_v1.py:63-67): y = maxpool(relu(bn(z))) =
 // relu(bn(maxpool(z))) because bn (rstd > 0) and relu are monotone - pool the raw fp32 pre-activations, then normalise only the
 // pooled values and write them as split planes.  The full-resolution activation is never materialised (saves one write and
@@ -787,6 +872,16 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
   const int64_t total = batch * ho * wo * (c / 8);
   DS_REQUIRE(total < (int64_t)1 << 31, "tensor too large for 32-bit indexing");
   if (total == 0) return 0;
+  if (k == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && ho == h && wo == w && ds::g_debug[8] != 1) {
+    int hseg = (int)h;
+    if (ds::g_debug[9] > 0) hseg = ds::g_debug[9];
+    const int nseg = (int)ds::cdiv(h, hseg);
+    const int64_t threads = batch * nseg * w * (c / 8);
+    maxpool_fwd_split_k3s1_walk_kernel<<<(unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, threads, (int)h, (int)w,
+                                                                                               (int)(c / 8), hseg, nseg, y_hi, y_lo, ldy, argmax);
+    DS_LAUNCH_CHECK();
+    return 0;
+  }
 #define DS_GO(KK, QQ)                                                                                                               \
   maxpool_fwd_split_simd_kernel<KK, QQ><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), \
       stride, pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax)
