@@ -248,6 +248,8 @@ int ds_colsum(const float* x, int64_t ldx, int64_t m, int64_t n, float* out, int
 int ds_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 /* dy *= (y > 0) */
 int ds_relu_bwd(float* dy, const float* y, int64_t n, void* stream);
+/* x = max(x, 0) in place (the ReLU of the joint model's fc layer, image_text_model/im_text_rnn_model.py:96, after its split-K GEMM) */
+int ds_relu(float* x, int64_t n, void* stream);
 int ds_round_tf32(float* x, int64_t n, void* stream);
 /* tf.train.AdamOptimizer (im_text_rnn_model.py:134): hyper (device) = {lr_t, beta1, beta2, eps, grad_scale};
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps), lr_t pre-corrected by the host */

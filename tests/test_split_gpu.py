@@ -14,11 +14,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(scope="module")
-def K():
+@pytest.fixture(scope="module", params=["cta-pairs", "single-cta"])
+def K(request):
+    """every test runs with the contraction kernel forced into CTA-pair mode (cta_group::2, 256-row tiles) and into single-CTA mode"""
     from tumblr_emotions_b200 import ops
+    from tumblr_emotions_b200._lib import lib
     ops.init(0)
-    return ops
+    lib().debug_set(10, 1 if request.param == "cta-pairs" else 2)
+    yield ops
+    lib().debug_set(10, 0)
 
 
 def gen(seed=0):

@@ -37,6 +37,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int ACC_COLS = 256;              // TMEM columns per accumulator buffer
 constexpr int THREADS = 192;
 constexpr int STG_BYTES = BM * 32 * 4;     // one epilogue staging tile: 128 rows x 32 fp32 columns
+constexpr bool DEFAULT_PAIR = true;        // CTA pairs (cta_group::2) by default
 
 struct Params {
   int64_t M, N, ldc;
@@ -73,7 +74,11 @@ __device__ __forceinline__ void tile_coords(const Params& p, int64_t t, int64_t&
   it1 = min(p.iters, it0 + p.ipz);
 }
 
-template <bool ROW_MODE>      // compile-time copy of p.row_mode: the generic path carries none of the stem's extra work
+// ROW_MODE: compile-time copy of p.row_mode - the generic path carries none of the stem's extra work.
+// PAIR: the CTAs of a 2-CTA cluster (one TPC) share 256 x BN tiles - cta_group::2 MMAs issued by the cluster's rank-0 CTA;
+// each CTA stages its own 128 rows of A but only HALF of the B tile, which cuts the L2 -> SM operand traffic (the kernel's
+// bound: ~46 B/clk per SM) by 25-33%.
+template <bool ROW_MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -81,7 +86,11 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t b_tile_bytes = (PAIR ? (uint32_t)p.bn >> 1 : (uint32_t)p.bn) * 128u;      // B rows staged by this CTA
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool cta_lead = rank == 0;                               // issues the MMAs of the pair
+  const int64_t work0 = PAIR ? blockIdx.x >> 1 : blockIdx.x;     // first work item / stride: per cluster in pair mode
+  const int64_t work_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   const uint32_t a_plane = ROW_MODE ? (uint32_t)p.tile_rows * 128u : (uint32_t)A_TILE_BYTES;       // bytes of one A plane in a ring slot
   const uint32_t stage_bytes = ROW_MODE ? 2u * a_plane : 2u * A_TILE_BYTES + 2u * b_tile_bytes;   // row mode: B is resident
   const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;   // epilogue staging tiles (1024-aligned, 16 KB each)
@@ -110,16 +119,17 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     mbar_init(bres_bar, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 4);      // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * b, PAIR ? 8 : 4);      // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * ACC_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, 2 * ACC_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 2 * ACC_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -156,9 +166,11 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           }
         }
       }
-      for (int64_t t = blockIdx.x; !ROW_MODE && t < p.tiles; t += gridDim.x) {
+      const uint32_t full_lead0 = PAIR ? mapa_shared(full0, 0) : full0;      // pair mode: every load signals the leader's barrier
+      for (int64_t t = work0; !ROW_MODE && t < p.tiles; t += work_step) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
+        if (PAIR) { m0 += rank * BM; n0 += (int)rank * (p.bn >> 1); }        // own rows of A, own half of the B tile
         int img = 0, hp = 0, wq = 0;
         if (p.ksize > 1) {
           const int64_t hw = (int64_t)p.h * p.w;
@@ -171,29 +183,50 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         int r = tap / p.ksize, sx = tap - r * p.ksize;
         for (int it = it0; it < it1; ++it) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, stage_bytes);
           const int c0 = cc * KC;
           const uint32_t sa = base + s * stage_bytes;
-          if (p.ksize == 1) {
-            tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
-            tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
-          } else {
-            tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
-            tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
-          }
           const int kb = tap * p.cin + c0;
-          tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
-          tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          if (PAIR) {
+            const uint32_t fb = full_lead0 + 8 * s;
+            if (cta_lead) mbar_expect_tx(full0 + 8 * s, 2u * stage_bytes);      // both CTAs' bytes land on this barrier
+            if (p.ksize == 1) {
+              tma_load_2d_pair(&tmAh, fb, sa, c0, (int32_t)m0);
+              tma_load_2d_pair(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
+            } else {
+              tma_load_im2col_4d_pair(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+              tma_load_im2col_4d_pair(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+            }
+            tma_load_2d_pair(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
+            tma_load_2d_pair(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          } else {
+            const uint32_t fb = full0 + 8 * s;
+            mbar_expect_tx(fb, stage_bytes);
+            if (p.ksize == 1) {
+              tma_load_2d(&tmAh, fb, sa, c0, (int32_t)m0);
+              tma_load_2d(&tmAl, fb, sa + A_TILE_BYTES, c0, (int32_t)m0);
+            } else {
+              tma_load_im2col_4d(&tmAh, fb, sa, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+              tma_load_im2col_4d(&tmAl, fb, sa + A_TILE_BYTES, c0, wq - p.pad, hp - p.pad, img, (uint16_t)sx, (uint16_t)r);
+            }
+            tma_load_2d(&tmBh, fb, sa + 2 * A_TILE_BYTES, kb, n0);
+            tma_load_2d(&tmBl, fb, sa + 2 * A_TILE_BYTES + b_tile_bytes, kb, n0);
+          }
           if (++cc == p.cpt) { cc = 0; ++tap; if (++sx == p.ksize) { sx = 0; ++r; } }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+      if (PAIR) {
+        // tail: every slot's last release (a multicast arrive from the leader) has landed before this CTA may retire
+        for (int i = 0; i < p.stages; ++i) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_lead) {
       // ---------------- MMA issuer ----------------
-      const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.bn);
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, (uint32_t)p.bn);
       uint32_t acc_it = 0;
       int s = 0; uint32_t ph = 0;
       const int nk_full = KC >> 4, nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;      // 16-channel steps per chunk
@@ -236,7 +269,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           }
         }
       }
-      for (int64_t t = blockIdx.x; !ROW_MODE && t < p.tiles; t += gridDim.x, ++acc_it) {
+      for (int64_t t = work0; !ROW_MODE && t < p.tiles; t += work_step, ++acc_it) {
         int64_t m0; int n0, it0, it1;
         tile_coords(p, t, m0, n0, it0, it1);
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -253,14 +286,20 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           for (int k = 0; k < nk; ++k) {
             const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
-            mma_f16(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
-            mma_f16(acc, dah, dbl, idesc, 1u);
-            mma_f16(acc, dah, dbh, idesc, 1u);
+            if (PAIR) {
+              mma_f16_pair(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
+              mma_f16_pair(acc, dah, dbl, idesc, 1u);
+              mma_f16_pair(acc, dah, dbh, idesc, 1u);
+            } else {
+              mma_f16(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
+              mma_f16(acc, dah, dbl, idesc, 1u);
+              mma_f16(acc, dah, dbh, idesc, 1u);
+            }
           }
-          mma_commit(empty0 + 8 * s);
+          if (PAIR) mma_commit_pair(empty0 + 8 * s); else mma_commit(empty0 + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        mma_commit(tfull0 + 8 * buf);
+        if (PAIR) mma_commit_pair(tfull0 + 8 * buf); else mma_commit(tfull0 + 8 * buf);
       }
     }
   } else {
@@ -276,7 +315,8 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     int n0_cta = 0;
     const int bands_per_img = ROW_MODE ? (p.rows_per_img + p.band_rows - 1) / p.band_rows : 1;
     int row_i = 0;                                      // row mode: output row within the current band
-    for (int64_t t = blockIdx.x; t < p.tiles; ++acc_it) {
+    const uint32_t tempty_lead0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
+    for (int64_t t = work0; t < p.tiles; ++acc_it) {
       int64_t m0; int n0, it0, it1;
       int band_nrows = 1;
       if (ROW_MODE) {
@@ -287,6 +327,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         n0 = 0; it0 = 0; it1 = 4;
       } else {
         tile_coords(p, t, m0, n0, it0, it1);
+        if (PAIR) m0 += rank * BM;
       }
       n0_cta = n0;
       const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -347,8 +388,8 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-      if (++row_i == band_nrows) { row_i = 0; t += gridDim.x; }      // next work item (row mode: next band after its last row)
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty_lead0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
+      if (++row_i == band_nrows) { row_i = 0; t += work_step; }      // next work item (row mode: next band after its last row)
     }
     if (do_stats) {
       // 4 warps x 32 rows -> one value per column (shared fp64 atomics, once per CTA), then one global atomic per column
@@ -372,13 +413,15 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+  if (PAIR) cluster_sync_all();           // both CTAs are done with the pair's tensor memory and barriers
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS); else tmem_dealloc(tmem_base, 2 * ACC_COLS); }
 }
 
-int pick_bn(int64_t m, int64_t n, int ksplit, int sms) {
-  // fewest column tiles (each a multiple of 32, <= 256, as even as possible); when that leaves SMs idle (small-M
-  // products such as the LSTM step) split N further, down to 32-wide tiles
-  const int64_t tiles_m = ((m + BM - 1) / BM) * ksplit;
+int pick_bn(int64_t row_tiles, int64_t n, int ksplit, int workers) {
+  // fewest column tiles (each a multiple of 32, <= 256, as even as possible); when that leaves workers (CTAs, or CTA
+  // pairs) idle (small-M products such as the LSTM step) split N further, down to 32-wide tiles
+  const int64_t tiles_m = row_tiles * ksplit;
+  const int sms = workers;
   int64_t tiles_n = (n + 255) / 256;
   while (tiles_m * tiles_n < sms && (n + tiles_n) / (tiles_n + 1) >= 32) ++tiles_n;
   int bn = (int)((n + tiles_n - 1) / tiles_n);
@@ -408,14 +451,23 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   if (ksplit > p.iters) ksplit = p.iters;
   p.ipz = (int)ds::cdiv(p.iters, ksplit);
   p.ksplit = (int)ds::cdiv(p.iters, p.ipz);
-  p.bn = ds::g_debug[1] > 0 ? ds::g_debug[1] : pick_bn(M, n, p.ksplit, sms);
+  // CTA pairs: 256-row tiles shared by the two CTAs of a cluster (each stages half of the B tile)
+  // (debug knob 10: 1 forces pairs wherever two row tiles exist, 2 forces single CTAs)
+  // Measured policy (tools/bench_conv.py): pairs pay off once a tile runs enough K iterations to hide the cross-SM barrier
+  // round trips - every 3x3 conv of the big maps, and 1x1 convs with >= 8 K chunks and wide column tiles; short-K,
+  // output-bound products (2b, Mixed_3 1x1) and the small-M GEMMs (LSTM steps, weight gradients) stay on single CTAs.
+  const bool pair_pays = ksize == 3 ? (M >= 37888 || n >= 192) : (p.ipz >= 8 && n >= 128 && M >= 37888);
+  const bool pair = ds::cdiv(M, BM) >= 2 && (ds::g_debug[10] == 1 || (ds::g_debug[10] == 0 && DEFAULT_PAIR && pair_pays));
+  const int64_t row_tiles = pair ? ds::cdiv(M, 2 * BM) : ds::cdiv(M, BM);
+  const int workers = pair ? sms / 2 : sms;
+  p.bn = ds::g_debug[1] > 0 ? ds::g_debug[1] : pick_bn(row_tiles, n, p.ksplit, workers);
   p.tiles_n = (int)ds::cdiv(n, p.bn);
   DS_REQUIRE(p.ksplit == 1 || !(flags & (DS_EPI_RELU | DS_EPI_STATS)), "split-K adds atomically: no ReLU / stats epilogue");
   DS_REQUIRE(!((flags & DS_EPI_ACCUMULATE) && (flags & (DS_EPI_RELU | DS_EPI_STATS))), "the accumulate epilogue is an in-L2 add: no ReLU / stats");
   DS_REQUIRE(p.bn % 32 == 0 && p.bn >= 32 && p.bn <= 256, "column tile must be a multiple of 32 in [32, 256]");
-  p.tiles = ds::cdiv(M, BM) * p.tiles_n * p.ksplit;
+  p.tiles = row_tiles * p.tiles_n * p.ksplit;
   p.h = (int)h; p.w = (int)w; p.pad = (ksize - 1) / 2;
-  p.row_mode = 0; p.tile_rows = BM; p.rows_per_img = 0; p.band_rows = 0;
+  p.row_mode = 0; p.tile_rows = pair ? 2 * BM : BM; p.rows_per_img = 0; p.band_rows = 0;
   const int64_t ktot = (int64_t)ksize * ksize * cin;
 
   CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
@@ -427,14 +479,15 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
     else r = ds::make_tmap_im2col_bf16(tm, ptr, (uint64_t)batch, (uint64_t)h, (uint64_t)w, (uint64_t)cin, (uint64_t)lda, ksize, p.pad, KC, BM);
   }
   if (r) return ds::fail("cuTensorMapEncode(A) failed: CUresult %d (M=%lld cin=%lld lda=%lld ks=%d)", r, (long long)M, (long long)cin, (long long)lda, ksize);
-  r = ds::make_tmap_2d_bf16(&tmBh, bt_hi, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)p.bn);
-  if (!r) r = ds::make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)p.bn);
+  const int b_rows = pair ? p.bn / 2 : p.bn;                      // B rows staged per CTA
+  r = ds::make_tmap_2d_bf16(&tmBh, bt_hi, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)b_rows);
+  if (!r) r = ds::make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)b_rows);
   if (r) return ds::fail("cuTensorMapEncode(B) failed: CUresult %d (n=%lld ktot=%lld ldb=%lld bn=%d)", r, (long long)n, (long long)ktot, (long long)ldb, p.bn);
 
   r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d (M=%lld n=%lld ldc=%lld)", r, (long long)M, (long long)n, (long long)ldc);
 
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_rows * 128;
   const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);      // alignment slack, barriers, stats reduction
   p.nstg = (226 * 1024 - fixed - 2 * STG_BYTES) / stage_bytes >= 2 ? 2 : 1;
   int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES) / stage_bytes;
@@ -447,15 +500,34 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   if (smem < 120 * 1024) smem = 120 * 1024;     // one CTA per SM: each CTA owns all 512 TMEM columns
   static bool attr_set = false;
   if (!attr_set) {
-    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  if (pair) {
+    // one cluster (CTA pair) per TPC; a cluster keeps the same column tile for all its tiles (see below)
+    int64_t nclusters = std::min<int64_t>(p.tiles, workers);
+    if (p.ksplit == 1 && p.tiles > nclusters && p.tiles_n <= nclusters) nclusters = nclusters / p.tiles_n * p.tiles_n;
+    DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= nclusters || nclusters % p.tiles_n == 0, "stats epilogue needs clusters % column tiles == 0");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ds::S(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ++ds::g_debug[15];
+    DS_CUDA(cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<false, true>, tmAh, tmAl, tmBh, tmBl, tmC, p));
+    return 0;
   }
   // a CTA must keep the same column tile for all its tiles (register-resident batch-norm partial sums): with tiles
   // ordered column-tile fastest that holds when the grid is a multiple of the column-tile count
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
-  conv_bf16x3_kernel<false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<false, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -517,9 +589,9 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + p.nstg * STG_BYTES + resident_b + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t grid = std::min<int64_t>(p.tiles, sms);
-  conv_bf16x3_kernel<true><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<true, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -98,6 +98,10 @@ __global__ void relu_bwd_kernel(float* __restrict__ dy, const float* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     if (!(y[i] > 0.f)) dy[i] = 0.f;
 }
+__global__ void relu_kernel(float* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = fmaxf(x[i], 0.f);
+}
 __global__ void round_tf32_kernel(float* __restrict__ x, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     x[i] = ds::to_tf32(x[i]);
@@ -170,6 +174,13 @@ int ds_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {
 int ds_relu_bwd(float* dy, const float* y, int64_t n, void* stream) {
   if (n == 0) return 0;
   relu_bwd_kernel<<<blocks_for(n), 256, 0, ds::S(stream)>>>(dy, y, n);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_relu(float* x, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  relu_kernel<<<blocks_for(n), 256, 0, ds::S(stream)>>>(x, n);
   DS_LAUNCH_CHECK();
   return 0;
 }

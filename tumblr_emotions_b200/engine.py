@@ -747,7 +747,9 @@ class Engine:
             self.text_fwd(train)
         if self.model == "joint":
             ops.copy2d(self.text_feat, View(self.concat, self.rnn_size, self.im_features))
-            ops.gemm_nn(View(self.concat), View(self.weight("W_fc")), View(self.dense), bias=self.weight("b_fc"), flags=ops.EPI_RELU)
+            # split-K (no ReLU epilogue) spreads the 256 x 512 x 1280 product over the SMs; the ReLU follows in place
+            ops.gemm_nn(View(self.concat), View(self.weight("W_fc")), View(self.dense), bias=self.weight("b_fc"))
+            ops.relu(self.dense)
             ops.gemm_nn(View(self.dense), View(self.weight("W_softmax")), self.logits_view(), bias=self.weight("b_softmax"))
         elif self.model == "text":
             ops.gemm_nn(self.text_feat, View(self.weight("W_softmax")), self.logits_view(), bias=self.weight("b_softmax"))

@@ -325,6 +325,10 @@ def axpy(y: torch.Tensor, x: torch.Tensor, alpha: float):
     lib().axpy(y.data_ptr(), x.data_ptr(), alpha, y.numel(), _stream())
 
 
+def relu(x: torch.Tensor):
+    lib().relu(x.data_ptr(), x.numel(), _stream())
+
+
 def relu_bwd(dy: torch.Tensor, y: torch.Tensor):
     lib().relu_bwd(dy.data_ptr(), y.data_ptr(), y.numel(), _stream())
 
