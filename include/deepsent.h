@@ -221,7 +221,8 @@ int ds_dropout_mask(float* mask, int64_t n, float keep, uint64_t seed, uint64_t*
 /* out[(t*batch + b), 0:dim] = table[ids[b,t], :], columns dim..ldo-1 zero-filled (bit-exact gather) */
 int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const int64_t* ids, int64_t batch,
                         int64_t steps, float* out, int64_t ldo, void* stream);
-/* one time step.  pre = zh + xw + bias, gate order i,j,f,o (BasicLSTMCell): c' = c*sig(f+fb)+sig(i)*tanh(j),
+/* one time step.  pre = zh + xw + bias (xw may be NULL: the recurrent product was accumulated onto the input projection
+ * and zh holds the sum), gate order i,j,f,o (BasicLSTMCell): c' = c*sig(f+fb)+sig(i)*tanh(j),
  * h' = tanh(c')*sig(o); rows with t >= seq_len carry (c,h) (dynamic_rnn semantics).  Saves the gate
  * activations [batch,4n] for BPTT.  h_hi/h_lo (optional, row stride ldh bf16 elements): split-bf16 copy of h_out, the operand
  * of the next step's recurrent contraction. */

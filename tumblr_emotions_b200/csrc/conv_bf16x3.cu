@@ -456,7 +456,8 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   // Measured policy (tools/bench_conv.py): pairs pay off once a tile runs enough K iterations to hide the cross-SM barrier
   // round trips - every 3x3 conv of the big maps, and 1x1 convs with >= 8 K chunks and wide column tiles; short-K,
   // output-bound products (2b, Mixed_3 1x1) and the small-M GEMMs (LSTM steps, weight gradients) stay on single CTAs.
-  const bool pair_pays = ksize == 3 ? (M >= 37888 || n >= 192) : (p.ipz >= 8 && n >= 128 && M >= 37888);
+  const bool pair_pays = ksize == 3 ? (M >= 37888 || n >= 192)
+                                    : (p.ipz >= 8 && n >= 128 && M >= 512 && (M >= 37888 || p.ksplit > 1 || p.ipz >= 16));
   const bool pair = ds::cdiv(M, BM) >= 2 && (ds::g_debug[10] == 1 || (ds::g_debug[10] == 0 && DEFAULT_PAIR && pair_pays));
   const int64_t row_tiles = pair ? ds::cdiv(M, 2 * BM) : ds::cdiv(M, BM);
   const int workers = pair ? sms / 2 : sms;

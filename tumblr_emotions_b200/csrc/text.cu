@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
     for (int g = 0; g < 4; ++g) {
       const int64_t off = b * 4 * n + (int64_t)g * n + u;
       const float4 a = *reinterpret_cast<const float4*>(zh + off);
-      const float4 x = *reinterpret_cast<const float4*>(xw + off);
+      const float4 x = xw ? *reinterpret_cast<const float4*>(xw + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + g * n + u));
       pre[g][0] = a.x + x.x + bb.x; pre[g][1] = a.y + x.y + bb.y; pre[g][2] = a.z + x.z + bb.z; pre[g][3] = a.w + x.w + bb.w;
     }

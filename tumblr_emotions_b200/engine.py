@@ -645,14 +645,17 @@ class Engine:
         else:
             ops.gemm_nn(View(self.E, e), View(kern[:e]), View(self.XW))
         for t in range(T):
+            xw = self.XW[t * B:(t + 1) * B]
             if self.split:
-                ops.gemm_bf16x3(SView(self.Hs[t]), self.whT, View(self.ZH))
-                hs = SView(self.Hs[t + 1])
+                # h_t x Wh is accumulated onto the step's input projection (split-K reduce-add in L2: a 2-way split halves
+                # the operand bytes each SM pulls for this small-M product); the gate kernel then reads one array
+                ops.gemm_bf16x3(SView(self.Hs[t]), self.whT, View(xw), flags=ops.EPI_ACCUMULATE, ksplit=2)
+                ops.lstm_gates_fwd(xw, None, bias, self.C[t], self.H[t], self.seq_lens, t, B, n, FORGET_BIAS,
+                                   self.G[t if train else 0], self.C[t + 1], self.H[t + 1], SView(self.Hs[t + 1]))
             else:
                 ops.gemm_nn(View(self.H[t]), View(kern[e:]), View(self.ZH))
-                hs = None
-            ops.lstm_gates_fwd(self.ZH, self.XW[t * B:(t + 1) * B], bias, self.C[t], self.H[t], self.seq_lens, t, B, n, FORGET_BIAS,
-                               self.G[t if train else 0], self.C[t + 1], self.H[t + 1], hs)
+                ops.lstm_gates_fwd(self.ZH, xw, bias, self.C[t], self.H[t], self.seq_lens, t, B, n, FORGET_BIAS,
+                                   self.G[t if train else 0], self.C[t + 1], self.H[t + 1], None)
 
     def text_bwd(self, dlast: View):
         B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
