@@ -246,6 +246,32 @@ def test_maxpool_split_stride1_ties_pick_first_tap(K, b, h, c):
     assert torch.equal(arg, arg32)
 
 
+@pytest.mark.parametrize("b,h,c,k,s", [(2, 28, 16, 3, 2), (3, 14, 48, 3, 2), (2, 56, 64, 3, 2), (2, 14, 8, 2, 2), (1, 7, 12, 3, 2), (2, 9, 8, 3, 2)])
+def test_fused_pool_bwd_bn_apply_matches_unfused(K, b, h, c, k, s):
+    """pool backward fused into the BN/ReLU backward (conv -> BN -> ReLU -> pool segments) == ds_maxpool_bwd followed by
+    ds_bn_relu_bwd_apply_split on the same argmax; even maps take the 2x2-block kernel, odd ones the per-pixel gather"""
+    g = gen(21)
+    m = b * h * h
+    z = torch.randn(m, c, generator=g)
+    mean, rstd, beta = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    y = F.relu((z - mean) * rstd + beta)
+    ho, pt, _ = O.tf_same_pad(h, k, s)
+    yp = torch.zeros(b * ho * ho, c, device=DEV)
+    arg = torch.zeros(b * ho * ho * c, dtype=torch.uint8, device=DEV)
+    K.maxpool_fwd(K.View(y.to(DEV)), b, h, h, c, k, s, pt, pt, ho, ho, K.View(yp), arg)
+    dyp = torch.randn(b * ho * ho, c, generator=g).to(DEV)
+    sums = (torch.randn(2 * c, generator=g).double() * m * 0.01).to(DEV)
+    zd, md, rd, bd = z.to(DEV), mean.to(DEV), rstd.to(DEV), beta.to(DEV)
+    dx = torch.zeros(m, c, device=DEV)
+    K.maxpool_bwd(K.View(dyp), arg, b, h, h, c, k, s, pt, pt, ho, ho, K.View(dx), accumulate=False)
+    dz1, dz2 = K.SView(K.new_split((m,), c, DEV)), K.SView(K.new_split((m,), c, DEV))
+    db1, db2 = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    K.bn_relu_bwd_apply_split(K.View(dx), K.View(zd), md, rd, bd, sums, c, dz1, db1)
+    K.maxpool_bwd_bn_apply_split(K.View(dyp), arg, K.View(zd), b, h, h, c, k, s, pt, pt, ho, ho, md, rd, bd, sums, c, dz2, db2)
+    close(dz2.torch(), dz1.torch(), 1e-6, "fused pool bwd + bn apply")
+    assert torch.equal(db1, db2)
+
+
 def test_avgpool_split(K):
     g = gen(12)
     b, hw, c = 3, 49, 1024

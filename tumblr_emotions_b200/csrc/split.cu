@@ -755,6 +755,93 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
   }
 }
 
+// 3x3 / stride 2 / no leading pad (even H, W - every TF-SAME pool of the tower): the 2x2 input pixels (2p..2p+1, 2q..2q+1) are
+// covered by the same four windows (p-1..p, q-1..q), so one thread handles the whole block: 4 argmax words and 4 pooled
+// gradients feed 4 output pixels (the per-pixel gather loads 16 + 16 with most of them predicated off), and the index
+// arithmetic is shared.  Same summation order as the per-pixel kernel.
+__device__ __forceinline__ void sel_acc(float g[4], uint32_t m, const float4& v) {
+  g[0] += (m & 0x000000ffu) ? v.x : 0.f;
+  g[1] += (m & 0x0000ff00u) ? v.y : 0.f;
+  g[2] += (m & 0x00ff0000u) ? v.z : 0.f;
+  g[3] += (m & 0xff000000u) ? v.w : 0.f;
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_k3s2_block_kernel(const float* __restrict__ dyp, int64_t lddy,
+                                                                              const uint8_t* __restrict__ argmax, const float* __restrict__ z,
+                                                                              int64_t ldz, int64_t B, int h, int w, int c4,
+                                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                              const float* __restrict__ beta, const double* __restrict__ sums,
+                                                                              int64_t sums_ld, uint16_t* __restrict__ dz_hi,
+                                                                              uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
+                                                                              int64_t arg_ld) {
+  const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= c4) return;
+  const int col = cg * 4;
+  const int ho = h >> 1, wo = w >> 1;
+  const int64_t b = blockIdx.y / (uint32_t)ho;
+  const int p = (int)(blockIdx.y - b * ho);
+  const double inv_m = 1.0 / ((double)B * h * w);
+  const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+  const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m1[j] = (float)(sums[col + j] * inv_m);
+    m2[j] = (float)(sums[sums_ld + col + j] * inv_m);
+  }
+  if (dbeta && blockIdx.y == 0 && threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dbeta[col + j] = (float)sums[col + j];
+  }
+  const bool up = p > 0;
+  const int64_t orow = (b * ho + p) * (int64_t)wo;               // pooled pixel (p, 0); the row above is orow - wo
+  const int64_t irow = (b * h + 2 * p) * (int64_t)w;             // input pixel (2p, 0)
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = threadIdx.y; q < wo; q += blockDim.y) {
+    const bool left = q > 0;
+    const int64_t o00 = orow + q;
+    const uint8_t* am = argmax + o00 * arg_ld + col;
+    const float* gp = dyp + o00 * lddy + col;
+    const uint32_t a00 = __ldg(reinterpret_cast<const uint32_t*>(am));
+    const uint32_t a01 = left ? __ldg(reinterpret_cast<const uint32_t*>(am - arg_ld)) : 0xfefefefeu;
+    const uint32_t a10 = up ? __ldg(reinterpret_cast<const uint32_t*>(am - wo * arg_ld)) : 0xfefefefeu;
+    const uint32_t a11 = (up && left) ? __ldg(reinterpret_cast<const uint32_t*>(am - (wo + 1) * arg_ld)) : 0xfefefefeu;
+    const float4 g00 = __ldg(reinterpret_cast<const float4*>(gp));
+    const float4 g01 = left ? __ldg(reinterpret_cast<const float4*>(gp - lddy)) : zero4;
+    const float4 g10 = up ? __ldg(reinterpret_cast<const float4*>(gp - wo * lddy)) : zero4;
+    const float4 g11 = (up && left) ? __ldg(reinterpret_cast<const float4*>(gp - (wo + 1) * lddy)) : zero4;
+    const int64_t pix = irow + 2 * q;
+    const float4 zv[4] = {__ldg(reinterpret_cast<const float4*>(z + pix * ldz + col)),
+                          __ldg(reinterpret_cast<const float4*>(z + (pix + 1) * ldz + col)),
+                          __ldg(reinterpret_cast<const float4*>(z + (pix + w) * ldz + col)),
+                          __ldg(reinterpret_cast<const float4*>(z + (pix + w + 1) * ldz + col))};
+    float g[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { g[i][0] = 0.f; g[i][1] = 0.f; g[i][2] = 0.f; g[i][3] = 0.f; }
+    // tap of input pixel (2p+dr, 2q+dc) in window (p-a, q-c): (dr + 2a, dc + 2c), valid while < 3
+    sel_acc(g[0], __vcmpeq4(a00, 0x00000000u), g00); sel_acc(g[0], __vcmpeq4(a01, 0x02020202u), g01);
+    sel_acc(g[0], __vcmpeq4(a10, 0x06060606u), g10); sel_acc(g[0], __vcmpeq4(a11, 0x08080808u), g11);
+    sel_acc(g[1], __vcmpeq4(a00, 0x01010101u), g00); sel_acc(g[1], __vcmpeq4(a10, 0x07070707u), g10);
+    sel_acc(g[2], __vcmpeq4(a00, 0x03030303u), g00); sel_acc(g[2], __vcmpeq4(a01, 0x05050505u), g01);
+    sel_acc(g[3], __vcmpeq4(a00, 0x04040404u), g00);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float zz[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (zz[j] - mu[j]) * rs[j];
+        const float gm = (xh + be[j] > 0.f) ? g[i][j] : 0.f;
+        out[j] = rs[j] * (gm - m1[j] - xh * m2[j]);
+      }
+      const int64_t px = pix + (i >> 1) * w + (i & 1);
+      ds::store4_split(dz_hi + px * lddz + col, dz_lo + px * lddz + col, out);
+    }
+  }
+}
+
 // HWIO fp32 -> forward operand [cout][kh][kw][cin] (row stride fwd_ld, filter-row stride fwd_rs >= kw*cin) and input-gradient
 // operand [cin][kh'][kw'][cout] (taps flipped; row stride dgrad_ld, tap stride dgrad_tap >= cout so that sibling 1x1 convs can share one fused operand),
 // each as hi / lo bf16 planes
@@ -980,6 +1067,14 @@ int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t*
   int cgs = std::min(c4, 64);
   while (c4 % cgs != 0 && cgs > 16) --cgs;                // widest x-extent <= 64 that divides the channel groups (or 16)
   const dim3 blk(cgs, std::max(1, 256 / cgs));
+  if (k == 3 && stride == 2 && pad_t == 0 && pad_l == 0 && h % 2 == 0 && w % 2 == 0 && ho == h / 2 && wo == w / 2 && ds::g_debug[8] != 1) {
+    const dim3 blocks2((unsigned)ds::cdiv(c4, cgs), (unsigned)(batch * ho));
+    maxpool_bwd_bn_apply_k3s2_block_kernel<<<blocks2, blk, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w, c4, mean, rstd,
+                                                                             beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta,
+                                                                             arg_ld > 0 ? arg_ld : c);
+    DS_LAUNCH_CHECK();
+    return 0;
+  }
   const dim3 blocks((unsigned)ds::cdiv(c4, cgs), (unsigned)(batch * h));
 #define DS_GO(KK, SS)                                                                                                              \
   maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, blk, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
