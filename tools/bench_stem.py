@@ -20,8 +20,9 @@ W = K.SView((torch.randn(N, 512, device=DEV) * 0.05).bfloat16())
 cs = [torch.empty(B * HO * HO, N, device=DEV) for _ in range(NBUF)]
 stats = torch.zeros(2 * N, dtype=torch.float64, device=DEV)
 byt = B * HO * pitch * 16 * 4 + B * HO * HO * N * 4
-for band in (4, 8, 14, 16, 28, 56, 112):
+for band, one_stg in ((16, 1), (16, 0), (28, 1), (28, 0), (8, 0), (56, 0)):
     lib().debug_set(7, band)
+    lib().debug_set(12, one_stg)
     f = lambda i: K.conv_s2d_rows(s_hi[i], s_lo[i], B, HO, HO, pitch, W, N, K.View(cs[i]), stats=stats)
     f(0)
     torch.cuda.synchronize()
@@ -32,5 +33,6 @@ for band in (4, 8, 14, 16, 28, 56, 112):
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 12
-    print("band %3d rows: %.3f ms  %.0f GB/s algorithmic" % (band, t, byt / t / 1e6), flush=True)
+    print("band %3d rows, %d staging tile(s): %.3f ms  %.0f GB/s algorithmic" % (band, 1 if one_stg else 2, t, byt / t / 1e6), flush=True)
 lib().debug_set(7, 0)
+lib().debug_set(12, 0)

@@ -257,9 +257,11 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 mma_f16(acc, dah, dbl, idesc, 1u);
                 mma_f16(acc, dah, dbh, idesc, 1u);
               }
+              // input row i feeds only this first filter-row group of output row i: release its slot right away, so the
+              // producer can refill it while the other three groups run
+              if (rr == 0) mma_commit(empty0 + 8 * s);
               if (++sr == p.stages) { sr = 0; phr ^= 1u; }
             }
-            mma_commit(empty0 + 8 * s);            // input row i is not needed by later output rows
             if (++s == p.stages) { s = 0; ph ^= 1u; }
             mma_commit(tfull0 + 8 * buf);
           }
@@ -583,7 +585,8 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   const int stage_bytes = 2 * (int)wout * 128;                    // a ring slot holds the two planes of one input row
   const int fixed = 1024 + 256 + 2 * p.bn * (int)sizeof(double);
   const int resident_b = 8 * p.bn * 128;
-  p.nstg = 1;
+  // two staging tiles (the epilogue of this short-K kernel is its critical path) if 4 ring slots still fit, else one
+  p.nstg = (226 * 1024 - fixed - 2 * STG_BYTES - resident_b) / stage_bytes >= 4 && ds::g_debug[12] != 1 ? 2 : 1;
   int stages = (226 * 1024 - fixed - p.nstg * STG_BYTES - resident_b) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   DS_REQUIRE(stages >= 4, "shared-memory budget exceeded: an output row needs its 4 input rows resident");
