@@ -124,6 +124,20 @@ int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t*
                                   int64_t h, int64_t w, int64_t c, int k, int stride, int pad_t, int pad_l, int64_t ho, int64_t wo,
                                   const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                   uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, int64_t arg_ld, void* stream);
+/* Grouped BN/ReLU backward: up to 4 segments with the same row count m (the branches of one inception block, whose output
+ * gradients become available together) in ONE launch each for the reductions and for the apply pass - same arithmetic as
+ * ds_bn_relu_bwd_reduce2 / ds_bn_relu_bwd_apply_split per segment.  `segs` is a HOST array, copied into the launch. */
+typedef struct ds_bn_segment {
+  const float* dy; int64_t lddy;       /* gradient w.r.t. the post-ReLU output [m, n] */
+  const float* z; int64_t ldz;         /* pre-activations [m, n] */
+  int64_t n;                           /* channels of this segment (multiple of 4) */
+  const float* mean; const float* rstd; const float* beta;
+  double* sums; int64_t sums_ld;       /* {sum g, sum g*xhat} at sums[c], sums[sums_ld + c] */
+  uint16_t* dz_hi; uint16_t* dz_lo; int64_t lddz;   /* apply pass: split-bf16 dz [m, n] */
+  float* dbeta;                        /* apply pass: beta gradient (may be NULL) */
+} ds_bn_segment;
+int ds_bn_relu_bwd_reduce2_grouped(const ds_bn_segment* segs, int count, int64_t m, void* stream);
+int ds_bn_relu_bwd_apply_split_grouped(const ds_bn_segment* segs, int count, int64_t m, void* stream);
 /* dbeta[c] = sums[c] (the frozen stem needs no dz: only its beta gradient) */
 int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream);
 int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h, int64_t w, int64_t c,

@@ -272,6 +272,35 @@ def test_fused_pool_bwd_bn_apply_matches_unfused(K, b, h, c, k, s):
     assert torch.equal(db1, db2)
 
 
+@pytest.mark.parametrize("m,widths", [(1000, (64, 16, 48, 24)), (392, (128,)), (5000, (208, 48, 64)), (37, (4, 8))])
+def test_grouped_bn_backward_matches_per_segment_launches(K, m, widths):
+    """ds_bn_relu_bwd_{reduce2,apply_split}_grouped over the branches of a block == one launch per branch (different channel counts,
+    strided slices of a shared gradient buffer, separate pre-activation buffers)"""
+    g = gen(31)
+    ctot = sum(widths)
+    dy_all = torch.randn(m, ctot, generator=g).to(DEV)              # the block's output gradient: segments are column slices
+    segs, singles, off = [], [], 0
+    for n in widths:
+        z = torch.randn(m, n, generator=g).to(DEV)
+        mean, rstd = (torch.randn(n, generator=g) * 0.1).to(DEV), (torch.rand(n, generator=g) + 0.5).to(DEV)
+        beta = (torch.randn(n, generator=g) * 0.3).to(DEV)
+        dy = K.View(dy_all, n, off)
+        s1, s2 = torch.zeros(2 * n, dtype=torch.float64, device=DEV), torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+        dz1, dz2 = K.SView(K.new_split((m,), n, DEV)), K.SView(K.new_split((m,), n, DEV))
+        db1, db2 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        K.bn_relu_bwd_reduce(dy, K.View(z), mean, rstd, beta, s1, n, fast=True)
+        K.bn_relu_bwd_apply_split(dy, K.View(z), mean, rstd, beta, s1, n, dz1, db1)
+        segs.append(K.bn_segment(dy, K.View(z), mean, rstd, beta, s2, n, dz2, db2))
+        singles.append((s1, s2, dz1, dz2, db1, db2, z, mean, rstd, beta))
+        off += n
+    K.bn_relu_bwd_reduce_grouped(segs, m)
+    K.bn_relu_bwd_apply_split_grouped(segs, m)
+    for s1, s2, dz1, dz2, db1, db2, *_ in singles:
+        close(s2, s1, 1e-6, "grouped sums")
+        close(dz2.torch(), dz1.torch(), 2e-5, "grouped dz")
+        close(db2, db1, 1e-6, "grouped dbeta")
+
+
 def test_avgpool_split(K):
     g = gen(12)
     b, hw, c = 3, 49, 1024

@@ -132,15 +132,15 @@ __global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __rest
 }
 
 // g = dy * [bn(z) > 0]; sums[c] += sum g, sums[sums_ld + c] += sum g * xhat
-__global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z,
-                                                             int64_t ldz, int64_t M, int64_t N, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, const float* __restrict__ beta,
-                                                             double* __restrict__ sums, int64_t sums_ld, int rows_per_cta) {
+// `valid`: this thread owns the 4 channels starting at `col` of the segment the pointers describe
+__device__ __forceinline__ void bn_bwd_reduce2_body(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z,
+                                                    int64_t ldz, int64_t M, bool valid, int64_t col, const float* __restrict__ mean,
+                                                    const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                    double* __restrict__ sums, int64_t sums_ld, int rows_per_cta) {
   const int cgs = blockDim.x, rl = blockDim.y;
-  const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  if (col < N) {
+  if (valid) {
     const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
     const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
     const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __rest
   for (int i = 0; i < 4; ++i) { red[t * 8 + i] = s[i]; red[t * 8 + 4 + i] = q[i]; }
   __syncthreads();
   // 8 values per column group (4 x sum g, 4 x sum g*xhat): thread (tx, ty < 8) folds value ty over the row lanes
-  if (col < N) {
+  if (valid) {
     for (int v = threadIdx.y; v < 8; v += rl) {
       double a = 0.0;
       for (int y = 0; y < rl; ++y) a += red[(y * cgs + threadIdx.x) * 8 + v];
@@ -185,16 +185,51 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __rest
   }
 }
 
-// dz = rstd * (g - sum(g)/m - xhat * sum(g*xhat)/m), g = dy * [bn(z) > 0]  -> split planes (z is left untouched)
-__global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __restrict__ dy, int64_t lddy,
-                                                                 const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
-                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 const float* __restrict__ beta, const double* __restrict__ sums,
-                                                                 int64_t sums_ld, uint16_t* __restrict__ dz_hi,
-                                                                 uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
-                                                                 int rows_per_cta) {
+__global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z,
+                                                             int64_t ldz, int64_t M, int64_t N, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                             double* __restrict__ sums, int64_t sums_ld, int rows_per_cta) {
   const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (col >= N) return;
+  bn_bwd_reduce2_body(dy, lddy, z, ldz, M, col < N, col, mean, rstd, beta, sums, sums_ld, rows_per_cta);
+}
+
+// Grouped launches: up to 4 segments with the same row count (the branches of an inception block, whose gradients become
+// available together) share one launch; the segments' channel groups are laid end to end along blockIdx.x / threadIdx.x.
+struct BnSegDev {
+  const float* dy; int64_t lddy; const float* z; int64_t ldz; int64_t n;
+  const float* mean; const float* rstd; const float* beta; double* sums; int64_t sums_ld;
+  uint16_t* dz_hi; uint16_t* dz_lo; int64_t lddz; float* dbeta;
+};
+struct BnSegsDev { BnSegDev s[4]; int count; };
+
+__device__ __forceinline__ bool bn_pick_segment(const BnSegsDev& g, int64_t cgroup, BnSegDev& out, int64_t& col) {
+  int64_t base = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < g.count) {
+      const int64_t ng = g.s[i].n >> 2;
+      if (!found && cgroup >= base && cgroup < base + ng) { out = g.s[i]; col = (cgroup - base) * 4; found = true; }
+      base += ng;
+    }
+  }
+  return found;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce2_grouped_kernel(const BnSegsDev g, int64_t M, int rows_per_cta) {
+  BnSegDev sg = g.s[0];
+  int64_t col = 0;
+  const bool valid = bn_pick_segment(g, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, sg, col);
+  bn_bwd_reduce2_body(sg.dy, sg.lddy, sg.z, sg.ldz, M, valid, col, sg.mean, sg.rstd, sg.beta, sg.sums, sg.sums_ld, rows_per_cta);
+}
+
+// dz = rstd * (g - sum(g)/m - xhat * sum(g*xhat)/m), g = dy * [bn(z) > 0]  -> split planes (z is left untouched)
+__device__ __forceinline__ void bn_bwd_apply_split_body(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z,
+                                                        int64_t ldz, int64_t M, int64_t col, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                        const double* __restrict__ sums, int64_t sums_ld,
+                                                        uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo, int64_t lddz,
+                                                        float* dbeta, int rows_per_cta) {
   const double inv_m = 1.0 / (double)M;
   const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
   const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
@@ -238,6 +273,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                                 const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ beta, const double* __restrict__ sums,
+                                                                 int64_t sums_ld, uint16_t* __restrict__ dz_hi,
+                                                                 uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
+                                                                 int rows_per_cta) {
+  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= N) return;
+  bn_bwd_apply_split_body(dy, lddy, z, ldz, M, col, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta, rows_per_cta);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_split_grouped_kernel(const BnSegsDev g, int64_t M, int rows_per_cta) {
+  BnSegDev sg = g.s[0];
+  int64_t col = 0;
+  if (!bn_pick_segment(g, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, sg, col)) return;
+  bn_bwd_apply_split_body(sg.dy, sg.lddy, sg.z, sg.ldz, M, col, sg.mean, sg.rstd, sg.beta, sg.sums, sg.sums_ld, sg.dz_hi, sg.dz_lo,
+                          sg.lddz, sg.dbeta, rows_per_cta);
 }
 
 __global__ void bn_dbeta_kernel(const double* __restrict__ sums, int n, float* __restrict__ dbeta) {
@@ -939,6 +994,44 @@ int ds_bn_relu_bwd_reduce2(const float* dy, int64_t lddy, const float* z, int64_
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 6, 128);
   bn_bwd_reduce2_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, g.rows_per_cta);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+static int bn_pack_segments(const ds_bn_segment* segs, int count, BnSegsDev& g, int64_t& n_total, bool need_dz) {
+  DS_REQUIRE(count >= 1 && count <= 4, "1..4 segments per grouped launch");
+  n_total = 0;
+  g.count = count;
+  for (int i = 0; i < count; ++i) {
+    const ds_bn_segment& a = segs[i];
+    DS_REQUIRE(a.n > 0 && a.n % 4 == 0 && a.ldz % 4 == 0 && a.lddy % 4 == 0 && (!need_dz || a.lddz % 4 == 0), "channel counts must be multiples of 4");
+    DS_REQUIRE((((uintptr_t)a.mean | (uintptr_t)a.rstd | (uintptr_t)a.beta | (uintptr_t)a.z | (uintptr_t)a.dy) & 15) == 0, "16-byte alignment");
+    DS_REQUIRE(a.sums != nullptr && (!need_dz || (a.dz_hi && a.dz_lo)), "missing segment buffers");
+    g.s[i] = BnSegDev{a.dy, a.lddy, a.z, a.ldz, a.n, a.mean, a.rstd, a.beta, a.sums, a.sums_ld, a.dz_hi, a.dz_lo, a.lddz, a.dbeta};
+    n_total += a.n;
+  }
+  for (int i = count; i < 4; ++i) g.s[i] = g.s[0];
+  return 0;
+}
+
+int ds_bn_relu_bwd_reduce2_grouped(const ds_bn_segment* segs, int count, int64_t m, void* stream) {
+  if (m == 0 || count == 0) return 0;
+  BnSegsDev g;
+  int64_t n_total = 0;
+  if (int rc = bn_pack_segments(segs, count, g, n_total, false)) return rc;
+  const RowGrid rg = row_grid(m, n_total, 6, 128);
+  bn_bwd_reduce2_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, rg.rows_per_cta);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_relu_bwd_apply_split_grouped(const ds_bn_segment* segs, int count, int64_t m, void* stream) {
+  if (m == 0 || count == 0) return 0;
+  BnSegsDev g;
+  int64_t n_total = 0;
+  if (int rc = bn_pack_segments(segs, count, g, n_total, true)) return rc;
+  const RowGrid rg = row_grid(m, n_total, 16);
+  bn_bwd_apply_split_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, rg.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -21,6 +21,7 @@ Data layout in HBM (per GPU, batch B):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -58,6 +59,8 @@ class ConvUnit:
         self.x, self.outs, self.dx, self.douts, self.segs, self.dx_accumulate = x, outs, dx, douts, seg_cols, dx_accumulate
         self.split = eng.split
         self.dbeta_pool = None          # frozen stem: beta gradient straight from the pooled map, nothing else
+        self.grouped_segs = ()          # segments whose BN backward (reduce + apply) a BlockBwdGroup launches ahead of bwd()
+        self.dz_region = None           # dZ buffer assigned by the group (else the shared scratch)
         # per output segment: (PoolNode, channel offset in the pooled map) when that segment feeds ONLY a max pool - then
         # maxpool(relu(bn(z))) = relu(bn(maxpool(z))) and the pool node applies BN + ReLU on the pooled pre-activations
         self.seg_pool = [None] * len(seg_cols)
@@ -176,7 +179,9 @@ class ConvUnit:
             ops.masked_colsum_split(self.dbeta_pool.dy, self.dbeta_pool.y, self.sums)
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
-        for (c, n), dy, sp in zip(self.segs, self.douts, self.seg_pool):
+        for si, ((c, n), dy, sp) in enumerate(zip(self.segs, self.douts, self.seg_pool)):
+            if si in self.grouped_segs:
+                continue
             if sp is not None:   # conv -> BN -> ReLU -> max pool: both BN reductions come off the pooled map (y - beta = xhat where y > 0)
                 pool, off = sp
                 ops.masked_colsum_split(pool.dy.slice(off, n), pool.y.slice(off, n), self.sums[c:], beta=self.beta[c:c + n], sums_ld=self.N)
@@ -187,8 +192,10 @@ class ConvUnit:
             ops.bn_dbeta(self.sums, self.N, self.dbeta)
             return
         if self.split:
-            dZ = SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
-            for (c, n), dy, sp in zip(self.segs, self.douts, self.seg_pool):
+            dZ = self.dz_region if self.dz_region is not None else SView(e.dz_scratch[:self.M * self.N * 2].view(self.M, 2 * self.N))
+            for si, ((c, n), dy, sp) in enumerate(zip(self.segs, self.douts, self.seg_pool)):
+                if si in self.grouped_segs:
+                    continue
                 if sp is not None:   # the pool's gradient routing fused into the BN backward pass over the full-resolution pre-activations
                     pool, off = sp
                     ops.maxpool_bwd_bn_apply_split(pool.dy.slice(off, n), pool.argmax, Zv.slice(c, n), B, pool.h_in, pool.h_in, n, pool.k,
@@ -234,6 +241,44 @@ class ConvUnit:
             chunks = -(-M // 64)
             ksplit = max(1, min(chunks, -(-2 * e.sm_count // tiles)))
             ops.gemm_bf16x3(At, Bt.rows_slice(c, n), View(g.view(kk * self.cin, n)), k=M, ksplit=ksplit)
+
+
+class BlockBwdGroup:
+    """BN/ReLU backward of everything in an inception block that reads the block's output gradient - the three leaf convs
+    and Branch_0's slice of the fused 1x1 unit - as ONE grouped reduction launch and ONE grouped apply launch (4 segments,
+    same pixel count) instead of 4 + 4; sits after the block's units in the node list, so it runs first in the backward pass."""
+
+    def __init__(self, eng, units_segs):
+        self.eng, self.units_segs = eng, units_segs          # [(ConvUnit, segment index)]
+        total, M = sum(u.N for u, _ in units_segs), units_segs[0][0].M
+        assert all(u.M == M for u, _ in units_segs)
+        self.M, self.elems = M, total * M * 2
+
+    def bind(self):
+        """carve the units' dZ buffers out of the shared scratch (the group's apply pass fills all of them at once)"""
+        # blocks whose output feeds a max pool (Mixed_3c, Mixed_4f) run their BN backward off the pooled map instead
+        self.enabled = all(u.seg_pool[si] is None for u, si in self.units_segs)
+        if not self.enabled:
+            return
+        off = 0
+        for u, si in self.units_segs:
+            u.dz_region = SView(self.eng.dz_scratch[off:off + u.M * u.N * 2].view(u.M, 2 * u.N))
+            u.grouped_segs = u.grouped_segs + (si,)
+            off += u.M * u.N * 2
+
+    def fwd(self, train):
+        pass
+
+    def bwd(self):
+        if not self.enabled:
+            return
+        segs = []
+        for u, si in self.units_segs:
+            c, n = u.segs[si]
+            segs.append(ops.bn_segment(u.douts[si], View(u.Z).slice(c, n), u.mean[c:c + n], u.rstd[c:c + n], u.beta[c:c + n],
+                                       u.sums[c:], u.N, u.dz_region.slice(c, n), u.dbeta[c:c + n]))
+        ops.bn_relu_bwd_reduce_grouped(segs, self.M)
+        ops.bn_relu_bwd_apply_split_grouped(segs, self.M)
 
 
 class PoolNode:
@@ -312,7 +357,8 @@ class Engine:
         self.has_image, self.has_text = model in ("joint", "image"), model in ("joint", "text")
         self.tower_classes = im_features if model == "joint" else nb_emotions
         self.bn_cursor, self.bn_index = 0, {}
-        self.nodes, self.units = [], []
+        self.nodes, self.units, self.groups = [], [], []
+        self.group_bn_bwd = os.environ.get("DS_GROUP_BN_BWD", "1") != "0"      # grouped BN-backward launches per inception block
         self.adam_t = 0
         self._graph = None
         self._bytes = 0
@@ -336,6 +382,8 @@ class Engine:
         self._layout_params()
         for u in self.units:
             u.bind()
+        for grp in self.groups:
+            grp.bind()
         if self.has_text:
             self._build_text()
         self._build_head()
@@ -417,6 +465,10 @@ class Engine:
                 # forward order; backward runs the reversed list, so the fused unit's input gradient (overwrite)
                 # must come *before* the pool's accumulate in reverse order -> pool is listed before u1
                 self.nodes += [pool, u1, u2, u3, u4]
+                if tr and self.split and self.group_bn_bwd:
+                    grp = BlockBwdGroup(self, [(u4, 0), (u3, 0), (u2, 0), (u1, 0)])
+                    self.nodes.append(grp); self.groups.append(grp)
+                    self.dz_elems = max(self.dz_elems, grp.elems // 2)
                 act, dact, c = vO, View(dOUT) if tr else None, ctot
                 producers = [(u1, 0, 0), (u2, 0, c0), (u3, 0, c0 + c1b), (u4, 0, c0 + c1b + c2b)]
         self.tower_out, self.d_tower_out, self.tower_c, self.tower_h = act, dact, c, h

@@ -6,6 +6,8 @@ whole step can be captured into a CUDA graph.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from ._lib import lib
@@ -153,6 +155,34 @@ def repack_conv_weights_split(hwio: torch.Tensor, fwd: SView = None, dgrad: SVie
     lib().repack_conv_weights_split(hwio.data_ptr(), kh, kw, cin, cout, fwd.ptr if fwd else 0, fwd.lo_ptr if fwd else 0,
                                     fwd.ld if fwd else 0, fwd_rs, dgrad.ptr if dgrad else 0, dgrad.lo_ptr if dgrad else 0,
                                     dgrad.ld if dgrad else 0, dgrad_tap if dgrad_tap is not None else cout, _stream())
+
+
+class BnSegment(ctypes.Structure):
+    """mirror of `ds_bn_segment` (include/deepsent.h)"""
+    _fields_ = [("dy", ctypes.c_void_p), ("lddy", ctypes.c_int64), ("z", ctypes.c_void_p), ("ldz", ctypes.c_int64), ("n", ctypes.c_int64),
+                ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("sums", ctypes.c_void_p),
+                ("sums_ld", ctypes.c_int64), ("dz_hi", ctypes.c_void_p), ("dz_lo", ctypes.c_void_p), ("lddz", ctypes.c_int64),
+                ("dbeta", ctypes.c_void_p)]
+
+
+def bn_segment(dy: View, z: View, mean, rstd, beta, sums, sums_ld, dz: SView = None, dbeta=None) -> BnSegment:
+    return BnSegment(dy.ptr, dy.ld, z.ptr, z.ld, z.cols, _p(mean), _p(rstd), _p(beta), _p(sums), sums_ld,
+                     dz.ptr if dz is not None else 0, dz.lo_ptr if dz is not None else 0, dz.ld if dz is not None else 0, _p(dbeta))
+
+
+def _seg_array(segs):
+    arr = (BnSegment * len(segs))(*segs)
+    return arr, ctypes.addressof(arr)
+
+
+def bn_relu_bwd_reduce_grouped(segs, m):
+    arr, addr = _seg_array(segs)
+    lib().bn_relu_bwd_reduce2_grouped(addr, len(segs), m, _stream())
+
+
+def bn_relu_bwd_apply_split_grouped(segs, m):
+    arr, addr = _seg_array(segs)
+    lib().bn_relu_bwd_apply_split_grouped(addr, len(segs), m, _stream())
 
 
 def bn_dbeta(sums, n, dbeta):
