@@ -101,18 +101,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """median SM clock / throttle reasons of the samples received in [t0, t1] (the timed region; nvidia-smi takes a few
+        hundred ms to start streaming, so it is started before the warm-up); if none fell inside, of the samples under load"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if t1 is not None and not any(t0 <= t <= t1 for t, _ in self.rows):
+            time.sleep(0.3)      # let a late first sample arrive rather than report none
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1] or [r for _, r in self.rows]
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -222,20 +227,22 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput (inputs already in HBM) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # before the warm-up: the sampler is already streaming when the timed region starts
     for _ in range(args.warmup):
         eng.train_step_graph(lr)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         eng.train_step_graph(lr)
     e1.record()
     barrier()
+    t_region1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     loss_resident = eng.total_loss()
     # ---- end to end: pinned-host inputs copied every step (prefetched on a copy stream while the previous step runs, then
     # moved into the step's input buffers device-to-device), loss read back every step ----
