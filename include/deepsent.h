@@ -29,7 +29,10 @@ const char* ds_last_error(void);
 int ds_init(int device);
 int ds_sm_count(void);
 /* development knobs (0 = default): key 0 = im2col base-coordinate convention, 1 = force N tile, 2 = force stages,
- * 3 = shared-memory budget per CTA in KB; key 15 (read-only use) counts the kernels launched by this library */
+ * 3 = shared-memory budget per CTA in KB, 7 = output rows per stem band, 8 = 1: generic (per-pixel gather) pooling kernels instead
+ * of the row-walking / 2x2-block ones, 9 = rows per segment of the row-walking pool kernels, 10 = CTA-pair mode of
+ * ds_conv_bf16x3 (1 force pairs, 2 force single CTAs), 12 = 1: single epilogue staging tile in the stem kernel;
+ * key 15 (read-only use) counts the kernels launched by this library */
 int ds_debug_set(int key, int value);
 int ds_debug_get(int key);
 

@@ -31,6 +31,28 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         lib.conv_bf16x3(0, 0, 8, 1, 1, 1, 8, 1, 0, 0, 8, 4, 0, 4, 0, 0, 0, 0, 1, 0)
 
 
+def test_bn_segment_struct_mirrors_the_header():
+    """ops.BnSegment (ctypes) must list the fields of `ds_bn_segment` (include/deepsent.h) in the same order with the same widths:
+    grouped BN launches pass a host array of these by address"""
+    import ctypes
+    import re
+    from tumblr_emotions_b200 import ops
+    from tumblr_emotions_b200._lib import HEADER
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct ds_bn_segment \{(.*?)\} ds_bn_segment;", text, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if decl:
+            m = re.match(r"(.*?)(\w+)$", decl)
+            fields.append((m.group(2), "*" in m.group(1), m.group(1).strip()))
+    got = ops.BnSegment._fields_
+    assert [f[0] for f in fields] == [g[0] for g in got]
+    for (name, is_ptr, ctype), (_, ct) in zip(fields, got):
+        assert ct is (ctypes.c_void_p if is_ptr else ctypes.c_int64), (name, ctype)
+    assert ctypes.sizeof(ops.BnSegment) == 8 * len(fields)          # all members are 8 bytes wide: no padding either side
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
