@@ -53,6 +53,22 @@ def test_bn_segment_struct_mirrors_the_header():
     assert ctypes.sizeof(ops.BnSegment) == 8 * len(fields)          # all members are 8 bytes wide: no padding either side
 
 
+def test_library_sass_uses_tcgen05_tma_and_cta_pairs():
+    """the built sm_100a library really contains the Blackwell paths: tcgen05.mma (UTCHMMA, single CTA and .2CTA), TMA tiled and
+    im2col loads, TMA stores and reduce-adds, tcgen05.commit (UTCBAR)"""
+    import shutil
+    import subprocess
+    from tumblr_emotions_b200._lib import LIB_PATH
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper() or "sm_100" in sass
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "UTMALDG.4D.IM2COL", "UTMALDG.4D.IM2COL.2CTA", "UTMASTG.2D", "UTMAREDG.2D.ADD",
+                     "UTCBAR", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
