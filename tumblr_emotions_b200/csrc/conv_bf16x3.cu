@@ -19,6 +19,14 @@
 //                     column over its warp's 32 rows into fp64 registers that live for the whole kernel (the grid is a
 //                     multiple of the column-tile count, so a CTA keeps the same output columns for all its tiles) and
 //                     are flushed with one global atomic per channel per CTA.
+// CTA-pair mode (template PAIR, clusters of two CTAs on one TPC; chosen per launch by the measured policy in ds_conv_bf16x3):
+//   the pair shares a 256 x BN tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (cp.async.bulk.tensor
+//   ...cta_group::2, every load completing on the rank-0 CTA's full barrier); the rank-0 CTA issues tcgen05.mma.cta_group::2
+//   (M = 256) into both CTAs' TMEM; tcgen05.commit...multicast::cluster releases ring slots and publishes accumulators in
+//   both CTAs; both epilogues arrive on the leader's TMEM-empty barrier.  The kernel's operand bound is the TMA row-request
+//   rate (one <=128-byte tile row per ~2.8 clk per SM); pairs remove half of the B rows per SM.
+// Row mode (template ROW_MODE, ds_conv_s2d_rows): the space-to-depth stem; weights resident in shared memory, work items are
+//   bands of consecutive output rows whose input rows pass through the ring once.
 // Replaces the slim.conv2d sites of image_model/inception_v1.py:71-247, their input gradients (same contraction on
 // flipped weights), the weight gradients of Mixed_5c (:229-248, as pixel-major GEMMs with split-K) and the LSTM
 // products of image_text_model/im_text_rnn_model.py:89-90.
