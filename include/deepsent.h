@@ -36,6 +36,11 @@ int ds_sm_count(void);
 int ds_debug_set(int key, int value);
 int ds_debug_get(int key);
 
+/* development probe, not on the product path (csrc/probe.cu): D[128,64] = rows [row_shift, row_shift + 128) of the 128B-swizzled
+ * shared-memory tile A[256,64] (bf16) times B[64,64]^T, with the UMMA descriptor's base-offset field left 0 (mode 0) or set to
+ * (start >> 7) & 7 (mode 1) - decides whether 3x3 taps can be read as shifted views of one staged halo tile */
+int ds_probe_umma_row_shift(const uint16_t* a, const uint16_t* b, int row_shift, int mode, float* d, void* stream);
+
 /* ---- dense contractions ---------------------------------------------------------------- */
 /* flags for the contraction epilogues */
 #define DS_EPI_RELU 1        /* out = max(out, 0)                        */

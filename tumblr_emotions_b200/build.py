@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeepsent.so")
-SOURCES = ["runtime.cu", "conv_tc.cu", "conv_bf16x3.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu"]
+SOURCES = ["runtime.cu", "conv_tc.cu", "conv_bf16x3.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
