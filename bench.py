@@ -192,13 +192,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
-    allreduce = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-
-        def allreduce(flat):
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 
     B = args.batch
     eng = Engine(model=args.model, batch=B, precision=args.precision, device=local, seed=0, world_size=world, dropout="rng",
@@ -214,9 +210,11 @@ def run_ours(args):
 
     feed(b0)
     if world > 1:
+        from tumblr_emotions_b200.api import make_comm
         dist.broadcast(eng.params, 0)
         eng.refresh_operands(everything=True)
-    eng.capture(allreduce)
+        eng.attach_comm(make_comm(rank, world))      # ds_comm: NCCL all-reduce behind the C ABI, captured inside the step graph
+    eng.capture()
     launches_per_step = eng.launches_per_step
     lr = 1e-3
 

@@ -28,18 +28,26 @@ const char* ds_last_error(void);
 /* binds the calling thread to `device`, resolves cuTensorMapEncode{Tiled,Im2col}, caches SM count */
 int ds_init(int device);
 int ds_sm_count(void);
-/* development knobs (0 = default): key 0 = im2col base-coordinate convention, 1 = force N tile, 2 = force stages,
- * 3 = shared-memory budget per CTA in KB, 7 = output rows per stem band, 8 = 1: generic (per-pixel gather) pooling kernels instead
- * of the row-walking / 2x2-block ones, 9 = rows per segment of the row-walking pool kernels, 10 = CTA-pair mode of
- * ds_conv_bf16x3 (1 force pairs, 2 force single CTAs), 12 = 1: single epilogue staging tile in the stem kernel;
- * key 15 (read-only use) counts the kernels launched by this library */
-int ds_debug_set(int key, int value);
-int ds_debug_get(int key);
+/* number of kernels this library has launched so far in the process (monotonic; host counter, no synchronisation): the
+ * benchmark's `gpu_launches` claim is the difference across one captured step */
+int ds_launch_count(void);
 
-/* development probe, not on the product path (csrc/probe.cu): D[128,64] = rows [row_shift, row_shift + 128) of the 128B-swizzled
- * shared-memory tile A[256,64] (bf16) times B[64,64]^T, with the UMMA descriptor's base-offset field left 0 (mode 0) or set to
- * (start >> 7) & 7 (mode 1) - decides whether 3x3 taps can be read as shifted views of one staged halo tile */
-int ds_probe_umma_row_shift(const uint16_t* a, const uint16_t* b, int row_shift, int mode, float* d, void* stream);
+/* ---- data-parallel collective (one process per GPU) --------------------------------------------------
+ * The reference's only multi-device precedent is slim/deployment/model_deploy.py: per-clone losses scaled by 1/num_clones
+ * (:220-223), the regularisation loss added once (:301-302), UPDATE_OPS of the first clone only (:352-355) and the gradients of
+ * the shared variables SUMMED across clones (:414-444).  A clone here is a rank: each rank reduces its flat gradient arena with
+ * ds_allreduce_sum_f32 (NCCL ring/NVLS all-reduce over NVLink; stream-ordered, CUDA-graph capturable, in place), then ds_adam
+ * applies grad_scale = 1/world.  NCCL is resolved at run time (dlopen): the library loads without it and these calls then fail.
+ *   ds_comm_unique_id: rank 0 creates the 128-byte rendezvous id, the host distributes it (torch.distributed / a file / MPI);
+ *   ds_comm_init: collective over all `world` ranks, binds to the calling thread's current device (call ds_init first);
+ *   ds_comm_destroy: frees the communicator (NULL is accepted). */
+typedef struct ds_comm ds_comm;
+int ds_comm_unique_id(uint8_t* id128);
+int ds_comm_init(ds_comm** comm, int rank, int world, const uint8_t* id128);
+int ds_allreduce_sum_f32(ds_comm* comm, float* buf, int64_t n, void* stream);
+int ds_comm_destroy(ds_comm* comm);
+/* NCCL_VERSION_CODE of the library resolved at run time, 0 when NCCL is not available */
+int ds_comm_nccl_version(void);
 
 /* ---- dense contractions ---------------------------------------------------------------- */
 /* flags for the contraction epilogues */
@@ -240,9 +248,12 @@ int ds_avgpool_dropout_bwd(const float* dout, int64_t ldo, int64_t batch, int64_
 int ds_dropout_mask(float* mask, int64_t n, float keep, uint64_t seed, uint64_t* counter, void* stream);
 
 /* ---- text tower (tf.nn.embedding_lookup + BasicLSTMCell/dynamic_rnn, im_text_rnn_model.py:82-92) */
-/* out[(t*batch + b), 0:dim] = table[ids[b,t], :], columns dim..ldo-1 zero-filled (bit-exact gather) */
+/* out[(t*batch + b), 0:dim] = table[ids[b,t], :], columns dim..ldo-1 zero-filled (bit-exact gather).
+ * An id outside [0, vocab) yields an all-zero row (what TF's GPU gather kernel does) AND, when oob_count != NULL, increments the
+ * device counter *oob_count: TF's CPU kernel - the reference's path - fails the step with InvalidArgument ("indices[..] is not in
+ * [0, vocab)"), so the host reads the counter at its next synchronisation point and raises (Engine.check_ids). */
 int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const int64_t* ids, int64_t batch,
-                        int64_t steps, float* out, int64_t ldo, void* stream);
+                        int64_t steps, float* out, int64_t ldo, int* oob_count, void* stream);
 /* one time step.  pre = zh + xw + bias (xw may be NULL: the recurrent product was accumulated onto the input projection
  * and zh holds the sum), gate order i,j,f,o (BasicLSTMCell): c' = c*sig(f+fb)+sig(i)*tanh(j),
  * h' = tanh(c')*sig(o); rows with t >= seq_len carry (c,h) (dynamic_rnn semantics).  Saves the gate

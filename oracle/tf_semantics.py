@@ -156,34 +156,36 @@ def bn_moving_update(moving: Tensor, batch: Tensor, decay: float = BN_DECAY) -> 
 
 
 def conv_bn_relu(x: Tensor, p: Dict[str, Tensor], scope: str, stride: int, is_training: bool,
-                 stats: Optional[dict]) -> Tensor:
+                 stats: Optional[dict], taps: Optional[dict] = None) -> Tensor:
     y = conv2d(x, p[scope + "/weights"], stride)
+    if taps is not None:
+        taps[scope] = y.detach()      # pre-activation (conv output before BN), for teacher-forced backward tests
     y = batch_norm(y, p[scope + "/BatchNorm/beta"], p[scope + "/BatchNorm/moving_mean"],
                    p[scope + "/BatchNorm/moving_variance"], is_training, stats, scope)
     return F.relu(y)
 
 
 def inception_v1_base(x: Tensor, p: Dict[str, Tensor], is_training: bool = True,
-                      final_endpoint: str = "Mixed_5c", stats: Optional[dict] = None):
+                      final_endpoint: str = "Mixed_5c", stats: Optional[dict] = None, taps: Optional[dict] = None):
     """image_model/inception_v1.py:29-251. x is NHWC."""
     end_points = {}
     net = x
     for item in SEQUENCE:
         kind, name = item[0], item[1]
         if kind == "conv":
-            net = conv_bn_relu(net, p, "InceptionV1/" + name, item[3], is_training, stats)
+            net = conv_bn_relu(net, p, "InceptionV1/" + name, item[3], is_training, stats, taps)
         elif kind == "maxpool":
             net = max_pool(net, item[2], item[3])
         else:
             c0, c1a, c1b, c2a, c2b, c3, b2 = MIXED[name]
             s = "InceptionV1/" + name
-            b0 = conv_bn_relu(net, p, s + "/Branch_0/Conv2d_0a_1x1", 1, is_training, stats)
-            b1 = conv_bn_relu(net, p, s + "/Branch_1/Conv2d_0a_1x1", 1, is_training, stats)
-            b1 = conv_bn_relu(b1, p, s + "/Branch_1/Conv2d_0b_3x3", 1, is_training, stats)
-            b2_ = conv_bn_relu(net, p, s + "/Branch_2/Conv2d_0a_1x1", 1, is_training, stats)
-            b2_ = conv_bn_relu(b2_, p, s + "/Branch_2/" + b2, 1, is_training, stats)
+            b0 = conv_bn_relu(net, p, s + "/Branch_0/Conv2d_0a_1x1", 1, is_training, stats, taps)
+            b1 = conv_bn_relu(net, p, s + "/Branch_1/Conv2d_0a_1x1", 1, is_training, stats, taps)
+            b1 = conv_bn_relu(b1, p, s + "/Branch_1/Conv2d_0b_3x3", 1, is_training, stats, taps)
+            b2_ = conv_bn_relu(net, p, s + "/Branch_2/Conv2d_0a_1x1", 1, is_training, stats, taps)
+            b2_ = conv_bn_relu(b2_, p, s + "/Branch_2/" + b2, 1, is_training, stats, taps)
             b3 = max_pool(net, 3, 1)
-            b3 = conv_bn_relu(b3, p, s + "/Branch_3/Conv2d_0b_1x1", 1, is_training, stats)
+            b3 = conv_bn_relu(b3, p, s + "/Branch_3/Conv2d_0b_1x1", 1, is_training, stats, taps)
             net = torch.cat([b0, b1, b2_, b3], dim=3)
         end_points[name] = net
         if name == final_endpoint:
@@ -193,13 +195,13 @@ def inception_v1_base(x: Tensor, p: Dict[str, Tensor], is_training: bool = True,
 
 def inception_v1(x: Tensor, p: Dict[str, Tensor], is_training: bool = True,
                  dropout_mask: Optional[Tensor] = None, stats: Optional[dict] = None,
-                 final_endpoint: str = "Mixed_5c"):
+                 final_endpoint: str = "Mixed_5c", taps: Optional[dict] = None):
     """image_model/inception_v1.py:254-309.  ``dropout_mask`` is the {0,1}
     keep mask [B,1,1,1024] (TF's RNG cannot be matched, so it is an input);
     None means keep everything *without* the 1/keep scaling being skipped:
     in training the output is still scaled by 1/0.8 only where a mask is given.
     """
-    net, end_points = inception_v1_base(x, p, is_training, final_endpoint, stats)
+    net, end_points = inception_v1_base(x, p, is_training, final_endpoint, stats, taps)
     net = avg_pool_valid(net, 7)
     end_points["AvgPool_0a_7x7"] = net
     if is_training and dropout_mask is not None:
@@ -252,19 +254,22 @@ def text_tower(ids: Tensor, seq_lens: Tensor, p: Dict[str, Tensor]) -> Tensor:
 
 def deep_sentiment_forward(images: Tensor, ids: Tensor, seq_lens: Tensor, p: Dict[str, Tensor],
                            is_training: bool = True, dropout_mask: Optional[Tensor] = None,
-                           stats: Optional[dict] = None):
+                           stats: Optional[dict] = None, taps: Optional[dict] = None):
     """DeepSentiment.__init__ graph (im_text_rnn_model.py:64-105). Returns (logits, concat_features)."""
-    img_feat, _ = inception_v1(images, p, is_training, dropout_mask, stats)
+    img_feat, _ = inception_v1(images, p, is_training, dropout_mask, stats, taps=taps)
     txt_feat = text_tower(ids, seq_lens, p)
     concat = torch.cat([img_feat, txt_feat], dim=1)
-    dense = F.relu(concat @ p["W_fc"] + p["b_fc"])
+    pre = concat @ p["W_fc"] + p["b_fc"]
+    if taps is not None:
+        taps["dense"] = pre.detach()
+    dense = F.relu(pre)
     logits = dense @ p["W_softmax"] + p["b_softmax"]
     return logits, concat
 
 
-def image_model_forward(images, p, is_training=True, dropout_mask=None, stats=None):
+def image_model_forward(images, p, is_training=True, dropout_mask=None, stats=None, taps=None):
     """ImageModel (im_model.py:159-164): tower logits are the model logits."""
-    logits, _ = inception_v1(images, p, is_training, dropout_mask, stats)
+    logits, _ = inception_v1(images, p, is_training, dropout_mask, stats, taps=taps)
     return logits
 
 
@@ -323,10 +328,12 @@ class TFAdam:
 
 
 def train_step(model: str, p: Dict[str, Tensor], opt: TFAdam, lr: float, batch: dict,
-               dropout_mask: Optional[Tensor] = None, unbiased_moving_var: bool = False):
+               dropout_mask: Optional[Tensor] = None, unbiased_moving_var: bool = False,
+               taps: Optional[dict] = None):
     """One slim.learning train_step: loss = xent + L2; grads; BN moving-average
     UPDATE_OPS; Adam.  ``model`` in {'joint','image','text'}.  Returns
-    (total_loss, logits, grads)."""
+    (total_loss, logits, grads).  ``taps`` (optional dict) receives every conv
+    pre-activation (keyed by scope) and the FC pre-activation ('dense')."""
     names = [k for k in opt.m]
     leaves = {k: p[k].detach().clone().requires_grad_(True) for k in names}
     q = dict(p)
@@ -334,9 +341,9 @@ def train_step(model: str, p: Dict[str, Tensor], opt: TFAdam, lr: float, batch: 
     stats: dict = {}
     if model == "joint":
         logits, _ = deep_sentiment_forward(batch["images"], batch["ids"], batch["seq_lens"], q, True,
-                                           dropout_mask, stats)
+                                           dropout_mask, stats, taps)
     elif model == "image":
-        logits = image_model_forward(batch["images"], q, True, dropout_mask, stats)
+        logits = image_model_forward(batch["images"], q, True, dropout_mask, stats, taps)
     else:
         logits = text_model_forward(batch["ids"], batch["seq_lens"], q)
     loss = softmax_cross_entropy(logits, batch["labels"])
@@ -351,6 +358,45 @@ def train_step(model: str, p: Dict[str, Tensor], opt: TFAdam, lr: float, batch: 
         p[scope + "/BatchNorm/moving_variance"] = bn_moving_update(p[scope + "/BatchNorm/moving_variance"], var)
     opt.step(p, grads, lr)
     return loss.detach(), logits.detach(), grads
+
+
+def train_step_clones(model: str, p: Dict[str, Tensor], opt: TFAdam, lr: float, batches: List[dict],
+                      dropout_masks: Optional[List[Optional[Tensor]]] = None):
+    """One training step deployed on N clones (slim/deployment/model_deploy.py): every clone runs the
+    graph on its own batch with its OWN batch-norm statistics; clone losses are scaled by 1/N
+    (:220-223), the regularisation loss is added once (:301-302), gradients of the shared variables
+    are summed (:414-444), the UPDATE_OPS (moving averages) are the first clone's (:352-355), and the
+    optimizer steps once.  Returns (total_loss, [per-clone xent], [per-clone logits], grads)."""
+    n = len(batches)
+    names = [k for k in opt.m]
+    leaves = {k: p[k].detach().clone().requires_grad_(True) for k in names}
+    q = dict(p)
+    q.update(leaves)
+    total, xents, logits_all, first_stats = 0.0, [], [], None
+    for c, batch in enumerate(batches):
+        mask = dropout_masks[c] if dropout_masks is not None else None
+        stats: dict = {}
+        if model == "joint":
+            logits, _ = deep_sentiment_forward(batch["images"], batch["ids"], batch["seq_lens"], q, True, mask, stats)
+        elif model == "image":
+            logits = image_model_forward(batch["images"], q, True, mask, stats)
+        else:
+            logits = text_model_forward(batch["ids"], batch["seq_lens"], q)
+        xent = softmax_cross_entropy(logits, batch["labels"])
+        total = total + xent / float(n)
+        xents.append(xent.detach())
+        logits_all.append(logits.detach())
+        if c == 0:
+            first_stats = stats
+    if model != "text":
+        total = total + regularization_loss(q)
+    gl = torch.autograd.grad(total, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(p[k])) for k, g in zip(names, gl)}
+    for scope, (mean, var, _) in first_stats.items():
+        p[scope + "/BatchNorm/moving_mean"] = bn_moving_update(p[scope + "/BatchNorm/moving_mean"], mean)
+        p[scope + "/BatchNorm/moving_variance"] = bn_moving_update(p[scope + "/BatchNorm/moving_variance"], var)
+    opt.step(p, grads, lr)
+    return total.detach(), xents, logits_all, grads
 
 
 def lr_at_step(step: int, initial_lr: float, decay_factor: float, num_samples: int, batch_size: int) -> float:

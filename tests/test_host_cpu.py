@@ -151,19 +151,101 @@ def test_synthetic_tfrecord_split_config1(tmp_path):
     d = str(tmp_path)
     T.write_synthetic_dataset(d, num_train=1000, num_valid=50, vocab_size=400001)
     assert len(T.split_files("train", d)) == 5
-    ds = open_split("train", d, {}, with_images=False)
-    assert ds.num_samples == 1000 and ds.num_classes == 15
+    with pytest.raises(IOError):                     # no GloVe file: the reference's open() fails, and so does the split
+        open_split("train", d, {'text_dir': d, 'emb_dir': 'embedding_weights', 'filename': 'glove.6B.50d.txt'}, with_images=False)
+    cfg = {'synthetic_embedding': True, 'vocab_size': 400001}
+    ds = open_split("train", d, cfg, with_images=False)
+    assert ds.num_samples == 1000 and ds.num_classes == 15 and ds.vocab_size == 400001
     b = ds.next_batch(32)
     assert b["ids"].shape == (32, 50) and b["ids"].dtype == torch.int64 and b["seq_lens"].dtype == torch.int64
     pos = torch.arange(50).unsqueeze(0)
     assert bool(((b["ids"] == 400000) == (pos >= b["seq_lens"].unsqueeze(1))).all())       # <ukn> padding past seq_len
     assert int(b["labels"].min()) >= 0 and int(b["labels"].max()) < 15
     # two ranks see disjoint records
-    r0 = open_split("train", d, {}, rank=0, world=2, with_images=False).next_batch(16)["post_ids"]
-    r1 = open_split("train", d, {}, rank=1, world=2, with_images=False).next_batch(16)["post_ids"]
+    r0 = open_split("train", d, cfg, rank=0, world=2, with_images=False).next_batch(16)["post_ids"]
+    r1 = open_split("train", d, cfg, rank=1, world=2, with_images=False).next_batch(16)["post_ids"]
     assert not set(r0.tolist()) & set(r1.tolist())
     with pytest.raises(ValueError):
         open_split("test", d, {})
+    # no silent substitution of synthetic posts for a missing split: the 'validation' shards of an empty directory
+    with pytest.raises(IOError, match="no TFRecord shards"):
+        open_split("validation", str(tmp_path / "nowhere"), {})
+    assert open_split("validation", str(tmp_path / "nowhere"), {'synthetic': True, 'num_samples': 8}).num_samples == 8
+
+
+def test_glove_loader_and_embedding_table(tmp_path):
+    """text_model/text_preprocessing.py:13-35 and the table of im_text_rnn_model.py:69-78: GloVe rows + a zero '<ukn>' row whose id
+    is the GloVe row count; the TFRecord split derives vocab_size from the file"""
+    from tumblr_emotions_b200 import tfrecord as T
+    from tumblr_emotions_b200.data import open_split
+    from tumblr_emotions_b200.text_preprocessing import _load_embedding_weights_glove, embedding_with_unknown_row
+    d = str(tmp_path)
+    os.makedirs(os.path.join(d, "text_model", "embedding_weights"))
+    rng = np.random.RandomState(0)
+    words = ["the", "happy", "sad", "dog", "cat-like", "@user", "sun"]
+    vecs = rng.randn(len(words), 50).astype(np.float32)
+    with open(os.path.join(d, "text_model", "embedding_weights", "glove.6B.50d.txt"), "w") as f:
+        for w, v in zip(words, vecs):
+            f.write(w + " " + " ".join(repr(float(x)) for x in v) + "\n")
+    vocabulary, emb = _load_embedding_weights_glove(os.path.join(d, "text_model"), "embedding_weights", "glove.6B.50d.txt")
+    assert vocabulary == words and emb.dtype == np.float32 and np.array_equal(emb, vecs)
+    word_to_id, table = embedding_with_unknown_row(vocabulary, emb)
+    assert table.shape == (8, 50) and not table[-1].any() and word_to_id['<ukn>'] == 7 and word_to_id['dog'] == 3
+    T.write_synthetic_dataset(d, num_train=20, num_valid=0, vocab_size=8, shards=2)
+    cfg = {'text_dir': os.path.join(d, "text_model"), 'emb_dir': 'embedding_weights', 'filename': 'glove.6B.50d.txt'}
+    ds = open_split("train", d, cfg, with_images=False)
+    assert ds.vocab_size == 8 and ds.embedding_dim == 50 and torch.equal(ds.embedding, torch.from_numpy(table))
+    with pytest.raises(IOError):
+        _load_embedding_weights_glove(d, "embedding_weights", "missing.txt")
+
+
+def test_paragraph_to_ids_follows_the_reference():
+    """text_model/text_preprocessing.py:84-105: lower-case, '#emotion' tags removed, punctuation (without '-' and '@') stripped,
+    unknown words and padding -> len(word_to_id), truncation to post_size"""
+    from tumblr_emotions_b200.text_preprocessing import _paragraph_to_ids
+    w2i = {"i": 0, "am": 1, "so": 2, "happy": 3, "today": 4, "well-being": 5, "@you": 6}
+    ids, n = _paragraph_to_ids("I am SO #happy, happy today!!! #sad (well-being) @you zzz", w2i, 12, ["happy", "sad"])
+    assert ids[:8] == [0, 1, 2, 3, 4, 5, 6, 7] and ids[8:] == [7] * 4 and n == 8
+    ids, n = _paragraph_to_ids("happy " * 20, w2i, 5, [])
+    assert ids == [3] * 5 and n == 5
+    ids, n = _paragraph_to_ids("", w2i, 4, ["happy"])
+    assert ids == [7] * 4 and n == 0
+
+
+def test_epoch_length_uses_the_global_batch():
+    """LR decay fires every epoch of the GLOBAL batch (ADVICE r1): num_samples // (batch * world), py2 integer division, >= 1"""
+    from tumblr_emotions_b200.api import epoch_batches
+    assert epoch_batches(1000, 32) == 31 and epoch_batches(1000, 32, 2) == 15 and epoch_batches(1000, 32, 8) == 3
+    assert epoch_batches(10, 64, 8) == 1
+    assert O.lr_at_step(31, 1e-3, 0.3, 1000, 32) == pytest.approx(3e-4)
+
+
+def test_tf1_central_crop_and_legacy_bilinear_resize():
+    """preprocess_for_eval (slim/preprocessing/inception_preprocessing.py:237-275) with TF-1.x semantics: central_crop start =
+    dim // 16 for fraction 0.875; resize_bilinear(align_corners=False) samples at dst * in/out (no half-pixel offset) - checked
+    against an independent scalar restatement, and shown to differ from torch's half-pixel F.interpolate"""
+    from tumblr_emotions_b200.tfrecord import tf1_central_crop_box, tf1_resize_bilinear
+    assert tf1_central_crop_box(500, 375, 0.875) == (31, 23, 438, 329)
+    assert tf1_central_crop_box(224, 224, 0.875) == (14, 14, 196, 196)
+    assert tf1_central_crop_box(10, 10, 1.0) == (0, 0, 10, 10)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(13, 9, 3, generator=g)
+    out_h, out_w = 7, 11
+    got = tf1_resize_bilinear(x, out_h, out_w)
+    ref = torch.zeros(out_h, out_w, 3)
+    for i in range(out_h):
+        sy = i * (13 / out_h)
+        y0 = int(np.floor(sy)); y1 = min(int(np.ceil(sy)), 12); fy = sy - y0
+        for j in range(out_w):
+            sx = j * (9 / out_w)
+            x0 = int(np.floor(sx)); x1 = min(int(np.ceil(sx)), 8); fx = sx - x0
+            top = x[y0, x0] + (x[y0, x1] - x[y0, x0]) * fx
+            bot = x[y1, x0] + (x[y1, x1] - x[y1, x0]) * fx
+            ref[i, j] = top + (bot - top) * fy
+    assert torch.allclose(got, ref, atol=1e-6)
+    assert torch.equal(tf1_resize_bilinear(x, 13, 9), x)                      # identity when the size does not change
+    half_pixel = torch.nn.functional.interpolate(x.permute(2, 0, 1)[None], size=(out_h, out_w), mode="bilinear", align_corners=False)[0].permute(1, 2, 0)
+    assert float((got - half_pixel).abs().max()) > 1e-2
 
 
 def test_synthetic_posts_follow_the_record_schema():
@@ -229,7 +311,7 @@ def _dp_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from tumblr_emotions_b200.api import gather_in_batch_order, make_allreduce
+        from tumblr_emotions_b200.api import exchange_bytes, gather_in_batch_order
         # (1) feature-extraction sharding: batch i lives on rank i % world; the gather restores single-process order
         nb_batches, bs, classes = 5, 4, 15
         full_l = torch.arange(nb_batches * bs * classes, dtype=torch.float32).view(nb_batches, bs, classes)
@@ -237,16 +319,15 @@ def _dp_worker(rank, world, port, q):
         mine = [i for i in range(nb_batches) if i % world == rank]
         l, y = gather_in_batch_order(full_l[mine].reshape(-1, classes), full_y[mine].reshape(-1), nb_batches, bs, world)
         ok1 = torch.equal(l, full_l.view(-1, classes)) and torch.equal(y, full_y.view(-1))
-        # (2) flat gradient all-reduce: sum over ranks, 1/world folded in afterwards == model_deploy's mean of clone gradients
-        g = torch.full((1000,), float(rank + 1))
-        make_allreduce(world)(g)
-        ok2 = bool((g / world == (1 + 2) / 2.0).all())
+        # (2) communicator rendezvous plumbing: rank 0's 128-byte id reaches every rank (the NCCL side of ds_comm_init needs GPUs)
+        uid = bytes(range(128))
+        ok2 = exchange_bytes(uid if rank == 0 else None) == uid
         q.put((rank, ok1, ok2))
     finally:
         dist.destroy_process_group()
 
 
-def test_world_size_2_gloo_sharding_and_allreduce():
+def test_world_size_2_gloo_sharding_and_rendezvous():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -284,3 +365,21 @@ def test_unknown_final_endpoint_raises_like_the_reference():
         Engine(model="image", batch=2, final_endpoint="Mixed_9z")
     with pytest.raises(ValueError, match="unknown model"):
         Engine(model="audio", batch=2)
+
+
+def test_clone_oracle_reduces_to_the_single_replica_step():
+    """O.train_step_clones (the checker of the N>1 GPU test): with one clone it IS train_step; without batch statistics (text model)
+    two half-batch clones reproduce the full-batch step - losses scaled by 1/N, gradients summed (model_deploy.py:220-223,414-444)"""
+    p = O.init_params(0, "text", vocab=101)
+    bd = O.synthetic_batch(8, seed=3, vocab=101, with_images=False)
+    names = O.trainable_names(p)
+    q1, q2, q3 = ({k: v.clone() for k, v in p.items()} for _ in range(3))
+    l1, lg1, g1 = O.train_step("text", q1, O.TFAdam(names, q1), 1e-3, bd, None)
+    halves = [{k: v[:4] for k, v in bd.items()}, {k: v[4:] for k, v in bd.items()}]
+    l2, xents, lg2, g2 = O.train_step_clones("text", q2, O.TFAdam(names, q2), 1e-3, halves, None)
+    l3, _, lg3, g3 = O.train_step_clones("text", q3, O.TFAdam(names, q3), 1e-3, [bd], None)
+    assert float(l1) == pytest.approx(float(l2), rel=1e-6) and float(l3) == float(l1)
+    assert torch.equal(lg3[0], lg1) and torch.allclose(torch.cat(lg2), lg1, atol=1e-6)
+    for n in names:
+        assert torch.equal(g3[n], g1[n]) and torch.allclose(g2[n], g1[n], rtol=1e-4, atol=1e-7), n
+        assert torch.equal(q3[n], q1[n])

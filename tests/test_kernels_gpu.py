@@ -266,6 +266,36 @@ def test_embedding_gather_bit_exact(K):
     assert float(out[:, dim:].abs().max()) == 0.0
 
 
+def test_embedding_gather_out_of_range_ids_are_reported(K):
+    """tf.nn.embedding_lookup on the reference's CPU path raises InvalidArgument for an id outside [0, vocab); the kernel writes a
+    zero row (TF's GPU behaviour), counts the offence, and Engine.check_ids raises at the next synchronisation point"""
+    g = gen(14)
+    vocab, dim, b, t = 101, 50, 3, 50
+    table = torch.randn(vocab, dim, generator=g)
+    ids = torch.randint(0, vocab, (b, t), generator=g)
+    ids[1, 3], ids[2, 7], ids[0, 0] = vocab, -1, 2 ** 40
+    out = torch.full((t * b, 64), 9.0, device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    K.embedding_gather(table.to(DEV), ids.to(DEV), K.View(out), cnt)
+    assert int(cnt.item()) == 3
+    rows = out.view(t, b, 64)
+    for bb, tt in ((1, 3), (2, 7), (0, 0)):
+        assert float(rows[tt, bb].abs().max()) == 0.0
+    ok = ids.clamp(0, vocab - 1)
+    ref = table[ok].permute(1, 0, 2)
+    keep = torch.ones(t, b, dtype=torch.bool); keep[3, 1] = keep[7, 2] = keep[0, 0] = False
+    assert torch.equal(rows[:, :, :dim].cpu()[keep], ref[keep])
+    from tumblr_emotions_b200.engine import Engine
+    eng = Engine(model="text", batch=b, vocab=vocab, dropout="none")
+    eng.set_batch(None, ids, torch.full((b,), 50), torch.zeros(b, dtype=torch.int64))
+    eng.train_step(1e-3)
+    with pytest.raises(IndexError, match="outside"):
+        eng.total_loss()
+    eng.set_batch(None, ok, torch.full((b,), 50), torch.zeros(b, dtype=torch.int64))
+    eng.train_step(1e-3)
+    assert eng.total_loss() > 0
+
+
 def test_lstm_sequence_forward_backward(K):
     """gates kernels + SIMT GEMMs chained over time vs oracle.basic_lstm and its autograd gradient"""
     g = gen(13)

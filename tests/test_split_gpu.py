@@ -18,11 +18,14 @@ DEV = "cuda:0"
 def K(request):
     """every test runs with the contraction kernel forced into CTA-pair mode (cta_group::2, 256-row tiles) and into single-CTA mode"""
     from tumblr_emotions_b200 import ops
-    from tumblr_emotions_b200._lib import lib
+    from tumblr_emotions_b200._lib import use_dev
+    dev = use_dev(True)              # libdeepsent_dev.so: the product objects + the launch-policy overrides (deepsent_dev.h)
     ops.init(0)
-    lib().debug_set(10, 1 if request.param == "cta-pairs" else 2)
+    dev.debug_set(10, 1 if request.param == "cta-pairs" else 2)
     yield ops
-    lib().debug_set(10, 0)
+    dev.debug_set(10, 0)
+    use_dev(False)
+    ops.init(0)
 
 
 def gen(seed=0):
@@ -352,6 +355,6 @@ def test_empty_inputs_are_no_ops(K):
                           K.SView(K.new_split((8,), 16, DEV)))
     from tumblr_emotions_b200._lib import lib
     lib().maxpool_bwd(0, 4, 0, 0, 7, 7, 8, 3, 1, 1, 1, 7, 7, 0, 8, 0, 0)
-    lib().embedding_gather(0, 10, 50, 0, 0, 50, 0, 64, 0)
+    lib().embedding_gather(0, 10, 50, 0, 0, 50, 0, 64, 0, 0)
     torch.cuda.synchronize()
     assert float(c.min()) == 7.0

@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 from tumblr_emotions_b200 import ops
-from tumblr_emotions_b200._lib import lib
+from tumblr_emotions_b200._lib import lib, use_dev
+use_dev(True)      # tuning tool: needs the launch-policy overrides of libdeepsent_dev.so
 
 dev = torch.device("cuda:0")
 ops.init(0)

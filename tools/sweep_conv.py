@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from tumblr_emotions_b200 import ops as K
-from tumblr_emotions_b200._lib import lib
+from tumblr_emotions_b200._lib import lib, use_dev
+use_dev(True)      # tuning tool: needs the launch-policy overrides of libdeepsent_dev.so
 
 K.init(0)
 DEV = "cuda:0"

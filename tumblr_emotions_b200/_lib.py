@@ -13,7 +13,9 @@ from typing import Dict, List, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "deepsent.h")
+DEV_HEADER = os.path.join(HERE, "..", "include", "deepsent_dev.h")
 LIB_PATH = os.path.join(HERE, "libdeepsent.so")
+DEV_LIB_PATH = os.path.join(HERE, "libdeepsent_dev.so")      # product objects + launch-policy overrides + hardware probe
 
 _CTYPE = {
     "int": ctypes.c_int,
@@ -50,7 +52,7 @@ def _to_ctype(ctype: str):
 class DeepSentLib:
     """Loads the shared library and exposes every `ds_*` entry point as a checked method."""
 
-    def __init__(self, path: str = LIB_PATH):
+    def __init__(self, path: str = LIB_PATH, dev: bool = False):
         if not os.path.exists(path):
             raise RuntimeError(
                 "libdeepsent.so not found at %s - run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -58,6 +60,9 @@ class DeepSentLib:
         import torch  # noqa: F401  (loads libcudart into the process before our library resolves it)
         self._dll = ctypes.CDLL(path)
         self.protos = parse_header()
+        self.dev = dev
+        if dev:
+            self.protos.update(parse_header(DEV_HEADER))
         self._dll.ds_last_error.restype = ctypes.c_char_p
         self._dll.ds_last_error.argtypes = []
         for name, (ret, args) in self.protos.items():
@@ -66,7 +71,7 @@ class DeepSentLib:
                 continue
             fn.restype = ctypes.c_int
             fn.argtypes = [_to_ctype(t) for t, _ in args]
-            if name in ("ds_version", "ds_sm_count", "ds_debug_get"):
+            if name in ("ds_version", "ds_sm_count", "ds_debug_get", "ds_launch_count", "ds_comm_nccl_version"):
                 setattr(self, name[3:], fn)
             else:
                 setattr(self, name[3:], self._checked(name, fn))
@@ -84,10 +89,29 @@ class DeepSentLib:
 
 
 _LIB = None
+_PRODUCT = None
+_DEV = None
 
 
 def lib() -> DeepSentLib:
-    global _LIB
+    """the library every wrapper in ops.py calls: the product build unless `use_dev(True)` switched to the development build"""
+    global _LIB, _PRODUCT
     if _LIB is None:
-        _LIB = DeepSentLib()
+        if os.environ.get("DS_DEV") == "1":
+            return use_dev(True)
+        _PRODUCT = _PRODUCT or DeepSentLib()
+        _LIB = _PRODUCT
+    return _LIB
+
+
+def use_dev(on: bool = True) -> DeepSentLib:
+    """Route the wrappers through libdeepsent_dev.so (adds ds_debug_set/get and the probe) or back to the product library.
+    The two libraries have separate state: call ops.init(device) after switching (Engine.__init__ does)."""
+    global _LIB, _PRODUCT, _DEV
+    if on:
+        _DEV = _DEV or DeepSentLib(DEV_LIB_PATH, dev=True)
+        _LIB = _DEV
+    else:
+        _PRODUCT = _PRODUCT or DeepSentLib()
+        _LIB = _PRODUCT
     return _LIB

@@ -1,4 +1,10 @@
-"""In-tree build of libdeepsent.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of libdeepsent.so for sm_100a (nvcc cross-compiles without a GPU).
+
+Two libraries come out of the same objects:
+  libdeepsent.so      the product: every symbol of include/deepsent.h, nothing else
+  libdeepsent_dev.so  the same objects + the launch-policy overrides (runtime.cu compiled with -DDS_DEV) and the hardware probe
+                      (probe.cu) declared in include/deepsent_dev.h - used only by tools/ and the tests that force a launch mode
+"""
 from __future__ import annotations
 
 import os
@@ -9,9 +15,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeepsent.so")
-SOURCES = ["runtime.cu", "conv_tc.cu", "conv_bf16x3.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu", "probe.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+LIB_DEV = os.path.join(HERE, "libdeepsent_dev.so")
+SOURCES = ["runtime.cu", "comm.cu", "conv_tc.cu", "conv_bf16x3.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu"]
+DEV_ONLY = ["probe.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -30,17 +37,17 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(HERE, "..", "include", "deepsent.h"))
+    headers += [os.path.join(HERE, "..", "include", "deepsent.h"), os.path.join(HERE, "..", "include", "deepsent_dev.h")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
 
-    def compile_one(src):
+    def compile_one(job):
+        src, obj, extra = job
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, obj)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + flags + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -48,13 +55,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         return o
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    jobs = [(s, s.replace(".cu", ".o"), []) for s in SOURCES]
+    jobs += [("runtime.cu", "runtime_dev.o", ["-DDS_DEV"])] + [(s, s.replace(".cu", ".o"), ["-DDS_DEV"]) for s in DEV_ONLY]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        objs = list(ex.map(compile_one, jobs))
+    prod = objs[:len(SOURCES)]
+    dev = [o for o in prod if not o.endswith("runtime.o")] + objs[len(SOURCES):]
+    for lib, members in ((LIB, prod), (LIB_DEV, dev)):
+        if force or _stale(lib, members):
+            cmd = [nvcc, "-shared", "-o", lib] + members + ["-lcudart", "-ldl"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     return LIB
 
 

@@ -10,6 +10,7 @@
 // One CTA: TMA-loads A [256 rows x 64 bf16] and B = [64 x 64] (the caller passes an identity matrix, so D = A_view), issues
 // 4 x tcgen05.mma (M = 128, N = 64, K = 16) on the view that starts `row_shift` rows into the tile, and writes D [128, 64] fp32.
 #include "common.cuh"
+#include "../../include/deepsent_dev.h"
 #include "ptx.cuh"
 #include "tmap.cuh"
 

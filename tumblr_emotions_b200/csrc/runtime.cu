@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include "common.cuh"
 #include "tmap.cuh"
+#ifdef DS_DEV
+#include "../../include/deepsent_dev.h"
+#endif
 
 namespace ds {
 
@@ -55,12 +58,18 @@ int ds_init(int device) {
 
 int ds_sm_count(void) { return ds::g_sm_count; }
 
+int ds_launch_count(void) { return ds::g_debug[15]; }
+
+#ifdef DS_DEV
+// development build only (libdeepsent_dev.so, include/deepsent_dev.h): launch-policy overrides for the tuning tools and the
+// per-kernel tests that force a mode.  The product library has no setter, so its policy table stays all-default.
 int ds_debug_set(int key, int value) {
-  if (key < 0 || key >= 16) return ds::fail("ds_debug_set: bad key %d", key);
+  if (key < 0 || key >= 15) return ds::fail("ds_debug_set: bad key %d", key);
   ds::g_debug[key] = value;
   return 0;
 }
 
 int ds_debug_get(int key) { return (key < 0 || key >= 16) ? 0 : ds::g_debug[key]; }
+#endif
 
 }  // extern "C"

@@ -9,7 +9,7 @@ namespace {
 // one warp per (t, b) row: 200-byte table rows -> float2 lanes, output row padded to ldo with zeros
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const float* __restrict__ table, int64_t vocab, int dim,
                                                                const int64_t* __restrict__ ids, int64_t B, int64_t T,
-                                                               float* __restrict__ out, int64_t ldo) {
+                                                               float* __restrict__ out, int64_t ldo, int* __restrict__ oob) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) embedding_gather_kernel(const float* __re
     const int64_t t = row / B, b = row - t * B;
     int64_t id = ids[b * T + t];
     const bool ok = id >= 0 && id < vocab;
+    if (!ok && oob && lane == 0) atomicAdd(oob, 1);      // reported to the host: TF's CPU kernel rejects such ids (InvalidArgument)
     const float2* src = reinterpret_cast<const float2*>(table + (ok ? id : 0) * dim);
     float2* dst = reinterpret_cast<float2*>(out + row * ldo);
     for (int j = lane; j < opairs; j += 32) {
@@ -161,12 +162,12 @@ int blocks_for(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_
 extern "C" {
 
 int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const int64_t* ids, int64_t batch, int64_t steps,
-                        float* out, int64_t ldo, void* stream) {
+                        float* out, int64_t ldo, int* oob_count, void* stream) {
   DS_REQUIRE(dim % 2 == 0 && ldo % 2 == 0 && ldo >= dim, "embedding rows are moved as float2");
   if (batch * steps == 0) return 0;
   const int64_t rows = batch * steps;
   const int blocks = (int)std::min<int64_t>(ds::cdiv(rows, 8), 148 * 16);
-  embedding_gather_kernel<<<blocks, 256, 0, ds::S(stream)>>>(table, vocab, (int)dim, ids, batch, steps, out, ldo);
+  embedding_gather_kernel<<<blocks, 256, 0, ds::S(stream)>>>(table, vocab, (int)dim, ids, batch, steps, out, ldo, oob_count);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -77,18 +77,17 @@ class SyntheticPosts:
 
 def open_split(split_name: str, dataset_dir: str, config: dict, rank: int = 0, world: int = 1, with_images: bool = True,
                with_text: bool = True):
-    """get_split_with_text(split_name, dataset_dir) analogue (datasets/convert_to_dataset.py:117).  Real TFRecord
-    splits are read by tumblr_emotions_b200.tfrecord when present; otherwise (or with config['synthetic']) the
-    synthetic generator stands in with the same fields."""
+    """get_split_with_text(split_name, dataset_dir) analogue (datasets/convert_to_dataset.py:117).  The TFRecord shards of the
+    split are read by tumblr_emotions_b200.tfrecord; a split without shards RAISES (TF's reader fails on the missing files) -
+    only an explicit config['synthetic'] = True substitutes the synthetic generator, which has the same fields."""
     if split_name not in ("train", "validation"):
         raise ValueError('split name %s was not recognized.' % split_name)      # convert_to_dataset.py:143-144
-    synthetic = config.get("synthetic")
-    if synthetic is None:
-        from .tfrecord import split_files
-        synthetic = not split_files(split_name, dataset_dir)
-    if not synthetic:
-        from .tfrecord import TFRecordPosts
-        return TFRecordPosts(split_name, dataset_dir, config, rank=rank, world=world, with_images=with_images)
+    if not config.get("synthetic", False):
+        from .tfrecord import TFRecordPosts, split_files
+        if not split_files(split_name, dataset_dir):
+            raise IOError("no TFRecord shards tumblr_%s_*.tfrecord under %s/tfrecords (set config['synthetic'] = True to run on "
+                          "synthetic posts)" % (split_name, dataset_dir))
+        return TFRecordPosts(split_name, dataset_dir, config, rank=rank, world=world, with_images=with_images, with_text=with_text)
     return SyntheticPosts(num_samples=int(config.get("num_samples", 1000)), num_classes=int(config.get("num_classes", 15)),
                           vocab_size=int(config.get("vocab_size", GLOVE_VOCAB + 1)), seed=1234 + rank + (0 if split_name == "train" else 7919),
                           with_images=with_images, with_text=with_text)

@@ -154,6 +154,13 @@ class ConvUnit:
                 ops.conv_simt(self.x, B, h, h, self.cin, 1, 1, 1, 0, 0, h, h, self.w_dgrad, self.N, Zv)
             if train:
                 ops.colstats(Zv, self.stats)
+        if train and e.z_override is not None:
+            # teacher-forced forward (parity tests of the backward pass): replace this unit's pre-activations by the given ones,
+            # so that every ReLU / max-pool gate downstream is the checker's and forward rounding does not reach the gradients
+            for s, c, n in self.scope_cols:
+                Zv.slice(c, n).torch().copy_(e.z_override[s].reshape(self.M, n))
+            self.stats.zero_()
+            ops.colstats(Zv, self.stats)
         if train and self.split:      # finalize (mean / rstd / moving averages) fused into the apply launch of each segment
             fl = ops.BN_UNBIASED if e.unbiased_moving_var else 0
             for (c, n), out, sp in zip(self.segs, self.outs, self.seg_pool):
@@ -346,6 +353,8 @@ class Engine:
         self.precision, self.world_size, self.dropout, self.unbiased_moving_var = precision, world_size, dropout, unbiased_moving_var
         self.training = training
         self.overlap_towers, self._side = overlap_towers, None
+        self.comm, self.first_frozen_boundary = None, None
+        self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         ops.init(device)
@@ -361,6 +370,7 @@ class Engine:
         self.group_bn_bwd = os.environ.get("DS_GROUP_BN_BWD", "1") != "0"      # grouped BN-backward launches per inception block
         self.adam_t = 0
         self._graph = None
+        self._infer_graph = None
         self._bytes = 0
 
         B = batch
@@ -465,6 +475,8 @@ class Engine:
                 # forward order; backward runs the reversed list, so the fused unit's input gradient (overwrite)
                 # must come *before* the pool's accumulate in reverse order -> pool is listed before u1
                 self.nodes += [pool, u1, u2, u3, u4]
+                if u1.trainable:      # backward reaches `pool` last within the block: every trainable weight gradient is final after it
+                    self.first_frozen_boundary = pool
                 if tr and self.split and self.group_bn_bwd:
                     grp = BlockBwdGroup(self, [(u4, 0), (u3, 0), (u2, 0), (u1, 0)])
                     self.nodes.append(grp); self.groups.append(grp)
@@ -479,7 +491,9 @@ class Engine:
 
     # -- parameters -------------------------------------------------------------------------------------------
     def _layout_params(self):
-        """Flat trainable arena: [L2-regularised conv weights | Logits bias | all BN betas (unit order) | LSTM | FC]."""
+        """Flat trainable arena: [L2-regularised conv weights | Logits bias | LSTM | FC | all BN betas (unit order)].  The betas
+        come last: their gradients are the only ones that become final late in the backward pass (the frozen layers still have a
+        beta each), so everything before them is reduced across ranks while that pass is still running (`backward`)."""
         tbl: List[Tuple[str, Tuple[int, ...]]] = []
         self.frozen_shapes: Dict[str, Tuple[int, ...]] = {}
         if self.has_image:
@@ -495,7 +509,6 @@ class Engine:
         if self.has_image:
             tbl.append(("InceptionV1/Logits/Conv2d_0c_1x1/biases", (self.tower_classes,)))
             self.n_bn = self.bn_cursor
-            tbl.append(("__betas__", (self.n_bn,)))
         if self.has_text:
             self.frozen_shapes["Text/W_embedding"] = (self.vocab, self.emb_dim)
             tbl.append(("Text/rnn/basic_lstm_cell/kernel", (self.emb_dim + self.rnn_size, 4 * self.rnn_size)))
@@ -505,6 +518,8 @@ class Engine:
                     ("W_softmax", (self.fc_size, self.nb_emotions)), ("b_softmax", (self.nb_emotions,))]
         elif self.model == "text":
             tbl += [("W_softmax", (self.rnn_size, self.nb_emotions)), ("b_softmax", (self.nb_emotions,))]
+        if self.has_image:
+            tbl.append(("__betas__", (self.n_bn,)))
         off, self.slots, self.l2_len = 0, {}, 0
         for i, (name, shp) in enumerate(tbl):
             n = int(math.prod(shp))
@@ -513,6 +528,7 @@ class Engine:
             if i == len(self.l2_names) - 1:
                 self.l2_len = off            # the L2-regularised conv weights form the arena prefix [0, l2_len)
         self.n_params = off
+        self.n_early = self.slots["__betas__"][0] if self.has_image else off      # arena prefix whose gradients are final early
         self.params, self.grads = self.new(off), self.new(off)
         self.adam_m, self.adam_v = self.new(off), self.new(off)
         self.hyper = self.new(8)
@@ -660,6 +676,7 @@ class Engine:
     def _build_text(self):
         B, T, n, tr = self.batch, self.post_size, self.rnn_size, self.training
         self.E = self.new(T * B, EMB_LD)
+        self.oob_ids = torch.zeros(1, dtype=torch.int32, device=self.device)      # ids outside [0, vocab) seen by the gather kernel
         self.XW = self.new(T * B, 4 * n)
         self.H, self.C = self.new(T + 1, B, n), self.new(T + 1, B, n)
         self.G = self.new(T, B, 4 * n) if tr else self.new(1, B, 4 * n)
@@ -689,7 +706,7 @@ class Engine:
         B, T, n, e = self.batch, self.post_size, self.rnn_size, self.emb_dim
         kern = self.weight("Text/rnn/basic_lstm_cell/kernel")
         bias = self.weight("Text/rnn/basic_lstm_cell/bias")
-        ops.embedding_gather(self.frozen["Text/W_embedding"], self.ids, View(self.E))
+        ops.embedding_gather(self.frozen["Text/W_embedding"], self.ids, View(self.E), self.oob_ids)
         # input projection for all time steps at once
         if self.split:
             ops.split_bf16(View(self.E), self.Es)
@@ -804,6 +821,8 @@ class Engine:
             ops.copy2d(self.text_feat, View(self.concat, self.rnn_size, self.im_features))
             # split-K (no ReLU epilogue) spreads the 256 x 512 x 1280 product over the SMs; the ReLU follows in place
             ops.gemm_nn(View(self.concat), View(self.weight("W_fc")), View(self.dense), bias=self.weight("b_fc"))
+            if train and self.z_override is not None:
+                self.dense.copy_(self.z_override["dense"])
             ops.relu(self.dense)
             ops.gemm_nn(View(self.dense), View(self.weight("W_softmax")), self.logits_view(), bias=self.weight("b_softmax"))
         elif self.model == "text":
@@ -818,6 +837,25 @@ class Engine:
         if self.has_image:
             ops.sumsq(self.params[:self.l2_len], 0.5 * WEIGHT_DECAY, self.loss_buf[2:3])
         ops.reduce_sum(self.loss_buf[1:4], 1.0, self.loss_buf[0:1])
+
+    # -- data-parallel collective (slim/deployment/model_deploy.py:414-444: gradients summed across clones) -------
+    def attach_comm(self, comm):
+        """`comm` is an ops.Comm (ds_comm behind the C ABI) over `world_size` ranks.  From now on `backward()` reduces the gradient
+        arena across ranks itself: everything except the BN betas on the side stream as soon as those gradients are final
+        (head, text tower, Logits, Mixed_5c), overlapped with the backward pass of the frozen layers, and the betas (7 280
+        floats) at the end."""
+        assert comm is None or comm.world == self.world_size
+        self.comm = comm
+
+    def _reduce_early(self):
+        """side stream: wait until the main stream has finished the last trainable layer's gradients, then all-reduce grads[:n_early]"""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self.comm.allreduce_sum(self.grads[:self.n_early])
 
     # -- backward --------------------------------------------------------------------------------------------
     def backward(self):
@@ -856,7 +894,15 @@ class Engine:
             ops.avgpool_dropout_bwd(View(self.dfeat), B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, self.d_tower_out)
             for node in reversed(self.nodes):
                 node.bwd()
-        if overlap:
+                if node is self.first_frozen_boundary and self.comm is not None:
+                    self._reduce_early()          # Mixed_5c / Logits / head (and, stream-ordered, the text tower) are final
+        if self.comm is not None:
+            if not self.has_image:
+                self.comm.allreduce_sum(self.grads)
+            else:
+                self._join()
+                self.comm.allreduce_sum(self.grads[self.n_early:])      # the BN beta gradients, final only now
+        elif overlap:
             self._join()
 
     # -- optimiser -------------------------------------------------------------------------------------------
@@ -883,46 +929,73 @@ class Engine:
         self.loss_and_grad()
         self.backward()
 
-    def train_step(self, lr: float, allreduce=None) -> None:
-        """one slim.learning train_step: loss, gradients, UPDATE_OPS, Adam (eager launch sequence)"""
+    def train_step(self, lr: float) -> None:
+        """one slim.learning train_step: loss, gradients (summed over ranks when a communicator is attached), UPDATE_OPS, Adam
+        (eager launch sequence)"""
         self.set_lr(lr)
         self.fwd_bwd()
-        if allreduce is not None:
-            allreduce(self.grads)
         self.apply_gradients()
         self.adam_t += 1
 
     # -- CUDA graph ----------------------------------------------------------------------------------------
-    def capture(self, allreduce=None):
-        """Capture the step into CUDA graphs (one when single-GPU; fwd+bwd | update around the all-reduce otherwise)."""
+    def _step_state(self):
+        """tensors a forward/backward pass mutates besides activations and gradients"""
+        return [self.moving_mean, self.moving_var, self.drop_counter] if self.has_image else []
+
+    def capture(self):
+        """Capture the whole step (forward, backward, the NCCL all-reduces when a communicator is attached, update) into ONE CUDA
+        graph: ncclAllReduce is stream-ordered and capturable, so the collective sits inside the graph on the side stream."""
         s = torch.cuda.Stream(priority=-1)      # image tower (critical path) above the side stream's text tower
         s.wait_stream(torch.cuda.current_stream())
+        # the warm-up must leave no trace: it would otherwise apply one extra BN moving-average update and advance the dropout
+        # counter, so that a captured run and an eager run of the same steps differ (slim runs UPDATE_OPS once per train step)
+        keep = [(t, t.clone()) for t in self._step_state()]
         with torch.cuda.stream(s):
             self.fwd_bwd()                      # warm-up outside capture (lazy module loading, attribute setting)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        for t, saved in keep:
+            t.copy_(saved)
         from ._lib import lib
-        n0 = lib().debug_get(15)
+        n0 = lib().launch_count()
         self._g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g1, stream=s):
+        # thread_local: other threads of the process (torch.distributed's watchdog) may touch CUDA while this thread captures
+        with torch.cuda.graph(self._g1, stream=s, capture_error_mode="thread_local"):
             self.fwd_bwd()
-            if allreduce is None:
-                self.apply_gradients()
-        self._g2 = None
-        if allreduce is not None:
-            self._g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g2):
-                self.apply_gradients()
-        self.launches_per_step = lib().debug_get(15) - n0      # kernels of this library inside one captured step
-        self._allreduce = allreduce
+            self.apply_gradients()
+        self.launches_per_step = lib().launch_count() - n0      # kernels of this library inside one captured step
         self._graph = True
+
+    def forward_only(self, train: bool = False):
+        """Forward pass of the batch in the input buffers with no update of any variable: the correlation_matrix / evaluate_* /
+        analysis path (im_text_rnn_model.py:171-207,342-376).  Inference mode is replayed from a CUDA graph captured on first
+        use; `train=True` (evaluate_*('train') builds the is_training graph but never runs UPDATE_OPS) runs eagerly and puts the
+        moving statistics and the dropout counter back."""
+        if train:
+            keep = [(t, t.clone()) for t in self._step_state()]
+            self.zero_step_buffers()
+            self.forward(train=True)
+            for t, saved in keep:
+                t.copy_(saved)
+            return
+        if self._infer_graph is None:
+            s = torch.cuda.Stream(priority=-1)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.forward(train=False)           # warm-up outside capture
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            from ._lib import lib
+            n0 = lib().launch_count()
+            self._infer_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._infer_graph, stream=s, capture_error_mode="thread_local"):
+                self.forward(train=False)
+            self.infer_launches = lib().launch_count() - n0
+        self._infer_graph.replay()
 
     def train_step_graph(self, lr: float):
         self.set_lr(lr)
         self._g1.replay()
-        if self._g2 is not None:
-            self._allreduce(self.grads)
-            self._g2.replay()
         self.adam_t += 1
 
     # -- input pipeline ---------------------------------------------------------------------------------------
@@ -963,8 +1036,20 @@ class Engine:
         if labels is not None:
             self.labels.copy_(labels, non_blocking=True)
 
+    def check_ids(self):
+        """tf.nn.embedding_lookup on the reference's CPU path fails the step on an id outside [0, vocab) (InvalidArgument); the
+        gather kernel counts such ids and this host check (a synchronisation point) raises for them"""
+        if self.has_text:
+            n = int(self.oob_ids.item())
+            if n:
+                self.oob_ids.zero_()
+                raise IndexError("%d token id(s) outside [0, %d) reached tf.nn.embedding_lookup (W_embedding has %d rows)"
+                                 % (n, self.vocab, self.vocab))
+
     def total_loss(self) -> float:
-        return float(self.loss_buf[0].item())
+        loss = float(self.loss_buf[0].item())
+        self.check_ids()
+        return loss
 
     def get_logits(self) -> torch.Tensor:
         return self.logits[:, :self.nb_emotions]

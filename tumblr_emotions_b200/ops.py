@@ -316,9 +316,10 @@ def dropout_mask(mask: torch.Tensor, keep: float, seed: int, counter: torch.Tens
 
 
 # ---- text ------------------------------------------------------------------------------------------
-def embedding_gather(table: torch.Tensor, ids: torch.Tensor, out: View):
+def embedding_gather(table: torch.Tensor, ids: torch.Tensor, out: View, oob_count: torch.Tensor = None):
     b, t = ids.shape
-    lib().embedding_gather(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), b, t, out.ptr, out.ld, _stream())
+    lib().embedding_gather(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), b, t, out.ptr, out.ld, _p(oob_count),
+                           _stream())
 
 
 def lstm_gates_fwd(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, n, forget_bias, gates, c_out, h_out, h_split: SView = None):
@@ -373,3 +374,38 @@ def adam(p, g, m, v, hyper):
 
 def fill_hyper(hyper, lr_t, beta1, beta2, eps, grad_scale):
     lib().fill_hyper(hyper.data_ptr(), lr_t, beta1, beta2, eps, grad_scale, _stream())
+
+
+# ---- data-parallel collective (NCCL behind the C ABI) ----------------------------------------------
+class Comm:
+    """`ds_comm*` handle: one communicator per process (one process per GPU).  `Comm.create(rank, world, exchange)` runs the
+    rendezvous: rank 0 makes the 128-byte NCCL unique id, `exchange(bytes_or_None) -> bytes` distributes it to every rank (the
+    host plumbing - torch.distributed broadcast, a file, ...), then every rank joins."""
+
+    def __init__(self, handle: int, rank: int, world: int):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        lib().comm_unique_id(ctypes.addressof(buf))
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, rank: int, world: int, exchange) -> "Comm":
+        uid = exchange(cls.unique_id() if rank == 0 else None)
+        assert len(uid) == 128
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(uid)
+        h = ctypes.c_void_p()
+        lib().comm_init(ctypes.addressof(h), rank, world, ctypes.addressof(buf))
+        return cls(h.value, rank, world)
+
+    def allreduce_sum(self, flat: torch.Tensor):
+        """in-place sum over ranks of a contiguous fp32 tensor, on torch's current stream"""
+        assert flat.dtype == torch.float32 and flat.is_contiguous()
+        lib().allreduce_sum_f32(self.handle, flat.data_ptr(), flat.numel(), _stream())
+
+    def destroy(self):
+        if self.handle:
+            lib().comm_destroy(self.handle)
+            self.handle = None

@@ -240,45 +240,77 @@ def write_synthetic_dataset(dataset_dir: str, num_train: int = 1000, num_valid: 
             f.write('%d:emotion_%d\n' % (i, i))
 
 
+def tf1_central_crop_box(h: int, w: int, central_fraction: float = 0.875):
+    """tf.image.central_crop of TF-1.x: offset = int(1 / ((1 - fraction) / 2)); start = dim // offset; size = dim - 2*start
+    (slim/preprocessing/inception_preprocessing.py:262-263 calls it with 0.875 -> start = dim // 16)."""
+    if central_fraction >= 1.0:
+        return 0, 0, h, w
+    off = int(1 / ((1 - central_fraction) / 2.0))
+    top, left = h // off, w // off
+    return top, left, h - 2 * top, w - 2 * left
+
+
+def tf1_resize_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """tf.image.resize_bilinear(align_corners=False) of TF-1.x on an HWC float tensor (inception_preprocessing.py:267-270): the
+    LEGACY sampling grid src = dst * (in / out) with no half-pixel offset - it differs from torch's
+    F.interpolate(align_corners=False) (half-pixel centres) by up to half an input pixel."""
+    in_h, in_w = x.shape[0], x.shape[1]
+
+    def grid(n_in, n_out):
+        src = torch.arange(n_out, dtype=torch.float64) * (n_in / float(n_out))
+        lo = src.floor().long().clamp(max=n_in - 1)
+        hi = src.ceil().long().clamp(max=n_in - 1)
+        return lo, hi, (src - src.floor()).to(x.dtype)
+
+    y0, y1, fy = grid(in_h, out_h)
+    x0, x1, fx = grid(in_w, out_w)
+    fy, fx = fy.view(-1, 1, 1), fx.view(1, -1, 1)
+    top = x[y0][:, x0] + (x[y0][:, x1] - x[y0][:, x0]) * fx
+    bot = x[y1][:, x0] + (x[y1][:, x1] - x[y1][:, x0]) * fx
+    return top + (bot - top) * fy
+
+
 def _preprocess_for_eval(jpeg: bytes, size: int = IMAGE_SIZE) -> torch.Tensor:
-    """slim inception preprocess_for_eval (slim/preprocessing/inception_preprocessing.py:237-275): central crop
-    87.5 %, bilinear resize to size x size, scale to [-1, 1]."""
+    """slim inception preprocess_for_eval (slim/preprocessing/inception_preprocessing.py:237-275): decode, convert to float in
+    [0, 1], TF-1.x central crop of 87.5 %, TF-1.x bilinear resize to size x size, then (x - 0.5) * 2 -> [-1, 1]."""
     from PIL import Image
     img = Image.open(io.BytesIO(jpeg)).convert("RGB")
     x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0)
-    h, w = x.shape[:2]
-    ch, cw = int(h * 0.875), int(w * 0.875)
-    top, left = (h - ch) // 2, (w - cw) // 2
-    x = x[top:top + ch, left:left + cw].permute(2, 0, 1).unsqueeze(0)
-    x = torch.nn.functional.interpolate(x, size=(size, size), mode="bilinear", align_corners=False)
-    return ((x[0].permute(1, 2, 0) - 0.5) * 2.0).contiguous()
+    top, left, ch, cw = tf1_central_crop_box(x.shape[0], x.shape[1], 0.875)
+    x = tf1_resize_bilinear(x[top:top + ch, left:left + cw], size, size)
+    return ((x - 0.5) * 2.0).contiguous()
 
 
 class TFRecordPosts:
     """A split read from the reference's TFRecord shards; records are sharded round-robin across ranks."""
 
-    def __init__(self, split_name: str, dataset_dir: str, config: dict, rank: int = 0, world: int = 1, with_images: bool = True):
+    def __init__(self, split_name: str, dataset_dir: str, config: dict, rank: int = 0, world: int = 1, with_images: bool = True,
+                 with_text: bool = True):
         self.files = split_files(split_name, dataset_dir)
         if not self.files:
             raise IOError("no TFRecord shards for split %r under %s" % (split_name, dataset_dir))
         self.num_samples = read_split_sizes(dataset_dir)[split_name]
         self.num_classes = len(read_label_file(dataset_dir))
-        self.vocab_size = int(config.get("vocab_size", 400001))
-        self.embedding_dim = 50
         self.with_images = with_images
         self.rank, self.world = rank, world
-        self._embedding = None
-        self._it = self._records()
-
-    @property
-    def embedding(self) -> torch.Tensor:
-        """stand-in for GloVe-6B-50d (embedding_weights/ is not shipped): N(0, 0.4^2), <ukn> row zero"""
-        if self._embedding is None:
+        # the frozen embedding table (im_text_rnn_model.py:69-78): GloVe rows + one zero row for '<ukn>' / padding.  Loaded from
+        # config[text_dir]/config[emb_dir]/config[filename]; a missing file raises, as the reference's open() does.  Only an
+        # explicit config['synthetic_embedding'] = True substitutes a seeded N(0, 0.4^2) table of config['vocab_size'] rows.
+        if not with_text:            # ImageModel never builds the table (image_model/im_model.py:139-164)
+            self.vocab_size, self.embedding_dim, self.embedding, self.word_to_id = 0, 0, None, None
+        elif config.get("synthetic_embedding"):
+            self.vocab_size, self.embedding_dim = int(config.get("vocab_size", 400001)), 50
             g = torch.Generator().manual_seed(4242)
             emb = torch.randn(self.vocab_size, self.embedding_dim, generator=g) * 0.4
             emb[-1] = 0.0
-            self._embedding = emb
-        return self._embedding
+            self.embedding, self.word_to_id = emb, None
+        else:
+            from .text_preprocessing import _load_embedding_weights_glove, embedding_with_unknown_row
+            vocabulary, glove = _load_embedding_weights_glove(config['text_dir'], config['emb_dir'], config['filename'])
+            self.word_to_id, table = embedding_with_unknown_row(vocabulary, glove)
+            self.embedding = torch.from_numpy(table)
+            self.vocab_size, self.embedding_dim = table.shape
+        self._it = self._records()
 
     def _records(self):
         i = 0
