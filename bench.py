@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the text tower on the main stream instead of a side stream")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch records of the contraction kernel pass (shape, ms, TFLOP/s) to this JSON file")
     return ap.parse_args()
 
 
@@ -273,7 +274,7 @@ def run_ours(args):
     # ---- dominant kernel: per-launch CUDA events around every tcgen05 contraction of an eager step ----
     roof = None
     if rank == 0 and not args.no_kernel_pass and args.precision == "bf16x3":
-        roof = kernel_pass(eng, ops, lr)
+        roof = kernel_pass(eng, ops, lr, args.dump_launches)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, threads = cpu_reference_step_time(args.model, args.cpu_batch, 2, 1)
@@ -310,7 +311,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_pass(eng, ops, lr):
+def kernel_pass(eng, ops, lr, dump=None):
     """One eager step with CUDA events around every ds_conv_bf16x3 launch on the launch stream: algorithmic FLOPs
     (2*M*N*K, counted once - the kernel issues 3 bf16 tensor-core passes per product) / their summed durations."""
     import torch
@@ -347,6 +348,11 @@ def kernel_pass(eng, ops, lr):
     finally:
         ops.conv_bf16x3, ops.conv_s2d_rows = orig, orig_stem
         eng.overlap_towers = overlap
+    if dump:
+        rows = [{"M": r[3][0], "K": r[3][1], "N": r[3][2], "ksize": r[3][3], "ms": r[0].elapsed_time(r[1]),
+                 "tflops_algorithmic": r[2] / r[0].elapsed_time(r[1]) / 1e9, "gbytes_per_s": r[4] / r[0].elapsed_time(r[1]) / 1e6} for r in recs]
+        with open(dump, "w") as f:
+            json.dump(rows, f, indent=0)
     tot_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
     tot_fl = sum(r[2] for r in recs)
     tot_bytes = sum(r[4] for r in recs)
