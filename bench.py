@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the text tower on the main stream instead of a side stream")
+    ap.add_argument("--overlap-comm", action="store_true", help="reduce the gradients early on the side stream (measured slower, see Engine.attach_comm)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch records of the contraction kernel pass (shape, ms, TFLOP/s) to this JSON file")
     a = ap.parse_args()
     if a.batch is None:
@@ -282,7 +283,7 @@ def run_ours(args):
         dist.broadcast(eng.params, 0)
         eng.refresh_operands(everything=True)
         if train:
-            eng.attach_comm(make_comm(rank, world))      # ds_comm: NCCL all-reduce behind the C ABI, captured inside the step graph
+            eng.attach_comm(make_comm(rank, world), overlap=args.overlap_comm)      # ds_comm: NCCL all-reduce behind the C ABI, captured inside the step graph
     if train:
         eng.capture()
         launches_per_step = eng.launches_per_step
@@ -419,9 +420,7 @@ def run_ours(args):
             line["parity"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
-        if eng.comm is not None:
-            torch.cuda.synchronize()
-            eng.comm.destroy()
+        eng.detach_comm()
         dist.destroy_process_group()
 
 

@@ -43,7 +43,7 @@ def _start_params():
     return p
 
 
-def _worker(rank, world, port, out_dir, graph):
+def _worker(rank, world, port, out_dir, graph, overlap):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
@@ -56,7 +56,7 @@ def _worker(rank, world, port, out_dir, graph):
         bd, mask = _inputs(rank)
         eng.set_batch(bd["images"], bd["ids"], bd["seq_lens"], bd["labels"])
         eng.drop_mask.copy_(mask)
-        eng.attach_comm(make_comm(rank, world))
+        eng.attach_comm(make_comm(rank, world), overlap=overlap)
         if graph:
             eng.capture()
             eng.train_step_graph(1e-3)
@@ -69,16 +69,16 @@ def _worker(rank, world, port, out_dir, graph):
                     "params": {n: eng.tensor(n).cpu().clone() for n in eng.variable_names() if n != "Text/W_embedding"}},
                    os.path.join(out_dir, "rank%d.pt" % rank))
         dist.barrier()
-        eng.comm.destroy()
+        eng.detach_comm()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graph", [True, False], ids=["cuda-graph", "eager"])
-def test_two_rank_step_equals_two_clone_oracle(tmp_path, graph):
+@pytest.mark.parametrize("graph,overlap", [(True, False), (False, False), (True, True)], ids=["cuda-graph", "eager", "cuda-graph-early-reduce"])
+def test_two_rank_step_equals_two_clone_oracle(tmp_path, graph, overlap):
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs %d GPUs" % WORLD)
-    mp.spawn(_worker, args=(WORLD, _free_port(), str(tmp_path), graph), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(WORLD, _free_port(), str(tmp_path), graph, overlap), nprocs=WORLD, join=True)
     res = [torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r)) for r in range(WORLD)]
     p = {k: v.double() for k, v in _start_params().items()}
     names = O.trainable_names(p)

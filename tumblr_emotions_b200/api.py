@@ -273,10 +273,7 @@ def _train(model_cls, config, checkpoints_dir, train_dir, num_steps, use_init_fn
     if rank == 0:
         save_checkpoint(eng, train_dir, step)
         print('Finished training. Last batch loss {0:.3f}'.format(total_loss))
-    if eng.comm is not None:
-        torch.cuda.synchronize()
-        eng.comm.destroy()
-        eng.attach_comm(None)
+    eng.detach_comm()
     return total_loss
 
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeepsent.so")
 LIB_DEV = os.path.join(HERE, "libdeepsent_dev.so")
-SOURCES = ["runtime.cu", "comm.cu", "conv_tc.cu", "conv_bf16x3.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu"]
+SOURCES = ["runtime.cu", "comm.cu", "conv_tc.cu", "conv_bf16x3.cu", "conv_halo.cu", "split.cu", "gemm_simt.cu", "bn.cu", "pool.cu", "text.cu", "misc.cu"]
 DEV_ONLY = ["probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

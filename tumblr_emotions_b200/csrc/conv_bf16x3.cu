@@ -452,6 +452,11 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   DS_REQUIRE(!(flags & DS_EPI_STATS) || stats != nullptr, "DS_EPI_STATS needs a stats buffer");
   const int64_t M = batch * h * w;
   if (M == 0 || n == 0) return 0;
+  // 3x3: the halo-tile kernel (conv_halo.cu) stages each activation tile once for all nine taps; it takes the launches whose
+  // im2col form is bound by operand row requests (dev knob 11: 1 forces the im2col path, 2 forces the halo path where it fits)
+  if (ksize == 3 && ksplit <= 1 && ds::g_debug[11] != 1 &&
+      (ds::g_debug[11] == 2 ? ds::conv3x3_halo_fits(batch, h, w, cin, n) : ds::conv3x3_halo_pays(batch, h, w, cin, n)))
+    return ds::conv3x3_halo_launch(a_hi, a_lo, lda, batch, h, w, cin, bt_hi, bt_lo, ldb, n, c, ldc, scale, bias, stats, flags, stream);
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   Params p;
   p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags;

@@ -353,7 +353,7 @@ class Engine:
         self.precision, self.world_size, self.dropout, self.unbiased_moving_var = precision, world_size, dropout, unbiased_moving_var
         self.training = training
         self.overlap_towers, self._side = overlap_towers, None
-        self.comm, self.first_frozen_boundary = None, None
+        self.comm, self.first_frozen_boundary, self.overlap_comm = None, None, False
         self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
@@ -839,13 +839,31 @@ class Engine:
         ops.reduce_sum(self.loss_buf[1:4], 1.0, self.loss_buf[0:1])
 
     # -- data-parallel collective (slim/deployment/model_deploy.py:414-444: gradients summed across clones) -------
-    def attach_comm(self, comm):
+    def attach_comm(self, comm, overlap: bool = False):
         """`comm` is an ops.Comm (ds_comm behind the C ABI) over `world_size` ranks.  From now on `backward()` reduces the gradient
-        arena across ranks itself: everything except the BN betas on the side stream as soon as those gradients are final
-        (head, text tower, Logits, Mixed_5c), overlapped with the backward pass of the frozen layers, and the betas (7 280
-        floats) at the end."""
+        arena across ranks itself, inside the step (and inside the step's CUDA graph): ONE all-reduce of the whole arena on the
+        main stream once the backward pass is complete.
+        `overlap=True` is the alternative schedule: everything except the BN betas is reduced on the side stream as soon as those
+        gradients are final (head, text tower, Logits, Mixed_5c), under the backward pass of the frozen layers, and the betas
+        (7 280 floats) at the end.  Measured on 2 x B200 (profiles/r02_comm_overlap.txt) it is SLOWER, 13.29 vs 13.0 ms per step:
+        the contraction kernels are persistent, one CTA per SM with ~200 KB of shared memory, so NCCL's CTAs cannot share an SM
+        with them - whichever contraction is launched while the collective holds its SMs finishes only after the collective does,
+        and the collective is serialised into the critical path with interest instead of being hidden."""
         assert comm is None or comm.world == self.world_size
-        self.comm = comm
+        self.comm, self.overlap_comm = comm, bool(overlap)
+
+    def detach_comm(self):
+        """Destroy the communicator.  NCCL keeps a communicator alive for as long as a CUDA graph that captured one of its
+        collectives exists (ncclCommDestroy blocks on those references), so the step graph is released first."""
+        if self.comm is None:
+            return
+        torch.cuda.synchronize()
+        self._g1, self._graph = None, None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        self.comm.destroy()
+        self.comm = None
 
     def _reduce_early(self):
         """side stream: wait until the main stream has finished the last trainable layer's gradients, then all-reduce grads[:n_early]"""
@@ -894,16 +912,15 @@ class Engine:
             ops.avgpool_dropout_bwd(View(self.dfeat), B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, self.d_tower_out)
             for node in reversed(self.nodes):
                 node.bwd()
-                if node is self.first_frozen_boundary and self.comm is not None:
+                if node is self.first_frozen_boundary and self.comm is not None and self.overlap_comm:
                     self._reduce_early()          # Mixed_5c / Logits / head (and, stream-ordered, the text tower) are final
-        if self.comm is not None:
-            if not self.has_image:
-                self.comm.allreduce_sum(self.grads)
-            else:
-                self._join()
-                self.comm.allreduce_sum(self.grads[self.n_early:])      # the BN beta gradients, final only now
-        elif overlap:
+        if overlap or (self.comm is not None and self.overlap_comm and self.has_image):
             self._join()
+        if self.comm is not None:
+            if self.overlap_comm and self.has_image:
+                self.comm.allreduce_sum(self.grads[self.n_early:])      # the BN beta gradients, final only now
+            else:
+                self.comm.allreduce_sum(self.grads)                     # the flat arena: one collective per step
 
     # -- optimiser -------------------------------------------------------------------------------------------
     def set_lr(self, lr: float):
