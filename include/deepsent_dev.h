@@ -21,6 +21,12 @@ int ds_debug_get(int key);
  * (mode 1) - decides whether 3x3 taps can be read as shifted views of one staged halo tile */
 int ds_probe_umma_row_shift(const uint16_t* a, const uint16_t* b, int row_shift, int mode, float* d, void* stream);
 
+/* hardware probe 2 (csrc/probe.cu): TMA cycles per box transfer for the access patterns of the contraction kernels - mode 0 2-D tiled
+ * load (64 x 128 rows), 1 4-D tiled halo load, 2 the same halo tile through an im2col-mode load with a padded bounding box, 3 the
+ * im2col kernel's 128-pixel tap load, 4 2-D tiled store, 5 4-D tiled clipped store.  `buf` is a device buffer viewed as a
+ * [images, h, w, ld] bf16 activation; out[grid] receives cycles per transfer of each CTA. */
+int ds_probe_tma_rate(void* buf, int mode, int64_t images, int64_t h, int64_t w, int64_t ld, int reps, int grid, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

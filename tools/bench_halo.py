@@ -22,6 +22,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--json", default=None)
+ap.add_argument("--only", default="", help="comma-separated substrings of the layer names to run")
+ap.add_argument("--eager", action="store_true", help="time eager launches (host launch overhead included) instead of a CUDA-graph replay")
 args = ap.parse_args()
 K.init(0)
 DEV = "cuda:0"
@@ -32,16 +34,33 @@ for name, hw in (("3b", 28), ("3c", 28), ("4b", 14), ("4c", 14), ("4d", 14), ("4
     c0, c1a, c1b, c2a, c2b, c3, _ = MIXED["Mixed_" + name]
     shapes += [(name + " b1 fwd", hw, c1a, c1b, 0), (name + " b1 dgrad", hw, c1b, c1a, 1), (name + " b2 fwd", hw, c2a, c2b, 0),
                (name + " b2 dgrad", hw, c2b, c2a, 1)]
+if args.only:
+    shapes = [sh for sh in shapes if any(k in sh[0] for k in args.only.split(","))]
 NBUF = 3
 
 
 def time_it(fn):
+    """GPU time per launch: `reps` launches on rotating buffers captured into one CUDA graph (no host launch gaps), replayed"""
     fn(0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.eager:
+        e0.record()
+        for i in range(args.reps):
+            fn(i % NBUF)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.reps * 1e3
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=s):
+        for i in range(args.reps):
+            fn(i % NBUF)
+    g.replay()
+    torch.cuda.synchronize()
     e0.record()
-    for i in range(args.reps):
-        fn(i % NBUF)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / args.reps * 1e3

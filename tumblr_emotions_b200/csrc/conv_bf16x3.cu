@@ -232,12 +232,14 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_lead) {
-      // ---------------- MMA issuer ----------------
+    if (cta_lead) {
+      // ---------------- MMA issuer: the whole warp walks the loops converged, the elected lane issues (ptx.cuh: mma3_f16) --------
+      const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, (uint32_t)p.bn);
       uint32_t acc_it = 0;
       int s = 0; uint32_t ph = 0;
       const int nk_full = KC >> 4, nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;      // 16-channel steps per chunk
+      const uint32_t a_plane16 = a_plane >> 4, a_tile16 = A_TILE_BYTES >> 4, b_tile16 = b_tile_bytes >> 4;
       if (ROW_MODE) {
         mbar_wait(bres_bar, 0);
         tc_fence_after();
@@ -256,25 +258,21 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             for (int rr = 0; rr < 4; ++rr) {
               mbar_wait(full0 + 8 * sr, phr);      // rows loaded for an earlier output row have completed already: returns at once
               tc_fence_after();
-              const uint32_t ah = base + sr * stage_bytes, al = ah + a_plane;
-              const uint32_t bh = bres + (uint32_t)(2 * rr) * b_tile_bytes, bl = bh + b_tile_bytes;
-              for (int k = 0; k < (KC >> 4); ++k) {
-                const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
-                const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
-                mma_f16(acc, dal, dbh, idesc, (rr > 0 || k > 0) ? 1u : 0u);
-                mma_f16(acc, dah, dbl, idesc, 1u);
-                mma_f16(acc, dah, dbh, idesc, 1u);
-              }
+              const uint32_t ah = umma_desc_lo(base + sr * stage_bytes), al = ah + a_plane16;
+              const uint32_t bh = umma_desc_lo(bres + (uint32_t)(2 * rr) * b_tile_bytes), bl = bh + b_tile16;
+#pragma unroll
+              for (int k = 0; k < (KC >> 4); ++k)
+                mma3_f16<false>(acc, ah + 2u * k, al + 2u * k, bh + 2u * k, bl + 2u * k, idesc, (rr > 0 || k > 0) ? 1u : 0u, elected);
               // input row i feeds only this first filter-row group of output row i: release its slot right away, so the
               // producer can refill it while the other three groups run
-              if (rr == 0) mma_commit(empty0 + 8 * s);
+              if (rr == 0) mma_commit_elected<false>(empty0 + 8 * s, elected);
               if (++sr == p.stages) { sr = 0; phr ^= 1u; }
             }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
-            mma_commit(tfull0 + 8 * buf);
+            mma_commit_elected<false>(tfull0 + 8 * buf, elected);
           }
           for (int j = 0; j < 3; ++j) {            // the three trailing input rows of the band
-            mma_commit(empty0 + 8 * s);
+            mma_commit_elected<false>(empty0 + 8 * s, elected);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -287,29 +285,24 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * ACC_COLS;
         int cc = it0 % p.cpt;
+        uint32_t accumulate = 0;
         for (int it = it0; it < it1; ++it) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const int nk = (cc == p.cpt - 1) ? nk_last : nk_full;
           if (++cc == p.cpt) cc = 0;
-          const uint32_t ah = base + s * stage_bytes, al = ah + A_TILE_BYTES, bh = al + A_TILE_BYTES, bl = bh + b_tile_bytes;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
-            const uint64_t dbh = umma_desc_k_sw128(bh + k * 32), dbl = umma_desc_k_sw128(bl + k * 32);
-            if (PAIR) {
-              mma_f16_pair(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
-              mma_f16_pair(acc, dah, dbl, idesc, 1u);
-              mma_f16_pair(acc, dah, dbh, idesc, 1u);
-            } else {
-              mma_f16(acc, dal, dbh, idesc, (it > it0 || k > 0) ? 1u : 0u);
-              mma_f16(acc, dah, dbl, idesc, 1u);
-              mma_f16(acc, dah, dbh, idesc, 1u);
+          const uint32_t ah = umma_desc_lo(base + s * stage_bytes), al = ah + a_tile16, bh = al + a_tile16, bl = bh + b_tile16;
+#pragma unroll
+          for (int k = 0; k < (KC >> 4); ++k) {
+            if (k < nk) {
+              mma3_f16<PAIR>(acc, ah + 2u * k, al + 2u * k, bh + 2u * k, bl + 2u * k, idesc, accumulate, elected);
+              accumulate = 1u;
             }
           }
-          if (PAIR) mma_commit_pair(empty0 + 8 * s); else mma_commit(empty0 + 8 * s);
+          mma_commit_elected<PAIR>(empty0 + 8 * s, elected);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (PAIR) mma_commit_pair(tfull0 + 8 * buf); else mma_commit(tfull0 + 8 * buf);
+        mma_commit_elected<PAIR>(tfull0 + 8 * buf, elected);
       }
     }
   } else {

@@ -137,10 +137,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuer: the whole warp walks the loops (converged), the elected lane issues ----------------
+    {
+      const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.bn);
       const int nk_last = (p.cin - (p.cpt - 1) * KC + 15) >> 4;
+      const uint32_t a_plane16 = a_plane >> 4, b_tile16 = b_tile >> 4;
       if (p.resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0, acc_it = 0;
       for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, ++acc_it) {
@@ -153,43 +155,43 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           mbar_wait(afull0 + 8 * sa, pha);
           tc_fence_after();
           const int nk = (cc == p.cpt - 1) ? nk_last : (KC >> 4);
-          const uint32_t slot = base + (uint32_t)sa * a_stage;
-          int arow = 0;                                   // r * Wp + s: the tap's shift on the padded grid, in 128-byte rows
-          for (int r = 0; r < 3; ++r, arow += p.Wp - 3) {
-            for (int s = 0; s < 3; ++s, ++arow) {
-              const int tap = r * 3 + s;
-              const uint32_t ah = slot + (uint32_t)arow * 128u, al = ah + a_plane;
-              uint32_t bh = 0;
-              if (!p.resident) {
+          const uint32_t slot_lo = umma_desc_lo(base + (uint32_t)sa * a_stage);
+          uint32_t arow8 = 0;                             // (r * Wp + s) * 128 B >> 4: the tap's shift on the padded grid
+          int koff = cc * KC;                             // resident weights: element tap * cin + cc * 64 of the dense K axis
+          for (int r = 0; r < 3; ++r, arow8 += (uint32_t)(p.Wp - 3) * 8u) {
+            for (int s = 0; s < 3; ++s, arow8 += 8u, koff += p.cin) {
+              const uint32_t ah = slot_lo + arow8, al = ah + a_plane16;
+              uint32_t bh;
+              if (p.resident) {
+                bh = umma_desc_lo(breg + (uint32_t)(2 * (koff >> 6)) * b_tile + (uint32_t)((koff & 63) << 1));
+              } else {
                 mbar_wait(bfull0 + 8 * sb, phb);
                 tc_fence_after();
-                bh = breg + (uint32_t)sb * 2u * b_tile;
+                bh = umma_desc_lo(breg + (uint32_t)sb * 2u * b_tile);
               }
-              for (int k = 0; k < nk; ++k) {
-                uint32_t bhk;
-                if (p.resident) {                         // dense K: element tap * cin + cc * 64 + 16 k of the weight row
-                  const int koff = tap * p.cin + cc * KC + (k << 4);
-                  bhk = breg + (uint32_t)(2 * (koff >> 6)) * b_tile + (uint32_t)((koff & 63) << 1);
-                } else {
-                  bhk = bh + (uint32_t)k * 32u;
+#pragma unroll
+              for (int k = 0; k < (KC >> 4); ++k) {
+                if (k < nk) {
+                  // dense K (resident): a tap whose 16-channel steps straddle two 64-element chunks re-derives the address
+                  uint32_t bk = bh + 2u * k;
+                  if (p.resident && ((koff & 63) + (k << 4)) >= 64) {
+                    const int ko = koff + (k << 4);
+                    bk = umma_desc_lo(breg + (uint32_t)(2 * (ko >> 6)) * b_tile + (uint32_t)((ko & 63) << 1));
+                  }
+                  mma3_f16<false>(acc, ah + 2u * k, al + 2u * k, bk, bk + b_tile16, idesc, accumulate, elected);
+                  accumulate = 1u;
                 }
-                const uint64_t dah = umma_desc_k_sw128(ah + k * 32), dal = umma_desc_k_sw128(al + k * 32);
-                const uint64_t dbh = umma_desc_k_sw128(bhk), dbl = umma_desc_k_sw128(bhk + b_tile);
-                mma_f16(acc, dal, dbh, idesc, accumulate);
-                mma_f16(acc, dah, dbl, idesc, 1u);
-                mma_f16(acc, dah, dbh, idesc, 1u);
-                accumulate = 1u;
               }
               if (!p.resident) {
-                mma_commit(bempty0 + 8 * sb);
+                mma_commit_elected<false>(bempty0 + 8 * sb, elected);
                 if (++sb == p.sb) { sb = 0; phb ^= 1u; }
               }
             }
           }
-          mma_commit(aempty0 + 8 * sa);
+          mma_commit_elected<false>(aempty0 + 8 * sa, elected);
           if (++sa == p.sa) { sa = 0; pha ^= 1u; }
         }
-        mma_commit(tfull0 + 8 * buf);
+        mma_commit_elected<false>(tfull0 + 8 * buf, elected);
       }
     }
   } else {

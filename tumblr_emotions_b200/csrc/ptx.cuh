@@ -250,6 +250,60 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// ---- warp-uniform issue of the split-bf16 product -------------------------------------------------------------------------
+// The MMA warp runs its loops with all 32 lanes converged and hands the elected lane's predicate to these blocks: an
+// `if (lane == 0) { tcgen05.mma ... }` region is divergent code, in which the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY
+// waterfall loop and rebuilds each descriptor with a dozen uniform-datapath instructions - measured ~120 clk per MMA on the issuing
+// thread (profiles/r02_ncu_halo_issue_bound.txt), i.e. narrow tiles (N <= 128: <= 64 clk of tensor work per MMA) were bound by
+// instruction issue, not by operands.  Descriptors travel as 32-bit words: only the start-address field (low word) changes.
+constexpr uint32_t UMMA_DESC_HI_SW128 = 0x40004040u;      // SBO 1024 B | version 1 | SWIZZLE_128B  (bits 32..63 of umma_desc_k_sw128)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | 0x10000u; }
+
+// acc (+)= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi for one 16-channel step; `elected` != 0 on exactly one lane of the converged warp
+template <bool PAIR>
+__device__ __forceinline__ void mma3_f16(uint32_t acc, uint32_t ah_lo, uint32_t al_lo, uint32_t bh_lo, uint32_t bl_lo, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t elected) {
+  if (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %7, %7;\n\t"
+        "mov.b64 dah, {%1, %8};\n\tmov.b64 dal, {%2, %8};\n\tmov.b64 dbh, {%3, %8};\n\tmov.b64 dbl, {%4, %8};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], dal, dbh, %5, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbl, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbh, %5, pt;\n\t}" ::"r"(acc),
+        "r"(ah_lo), "r"(al_lo), "r"(bh_lo), "r"(bl_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, %7, %7;\n\t"
+        "mov.b64 dah, {%1, %8};\n\tmov.b64 dal, {%2, %8};\n\tmov.b64 dbh, {%3, %8};\n\tmov.b64 dbl, {%4, %8};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %5, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %5, pt;\n\t}" ::"r"(acc),
+        "r"(ah_lo), "r"(al_lo), "r"(bh_lo), "r"(bl_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
+  }
+}
+// tcgen05.commit by the elected lane of a converged warp (the lane that issued the MMAs)
+template <bool PAIR>
+__device__ __forceinline__ void mma_commit_elected(uint32_t bar, uint32_t elected) {
+  if (PAIR) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %1, 0;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
+        "r"(elected), "h"(mask)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %1, 0;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+        "r"(elected)
+        : "memory");
+  }
+}
+
 // instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, both K-major, N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
