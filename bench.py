@@ -439,7 +439,9 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
         flags = kw.get("flags", 0)
         # algorithmic bytes: A and B read once (4 bytes per split value), C written once (read too by the accumulate epilogue)
         nbytes = 4.0 * (batch * h * w * cin + n * ksize * ksize * cin + batch * h * w * n * (2 if flags & ops.EPI_ACCUMULATE else 1))
-        recs.append((s, e, 2.0 * batch * h * w * ksize * ksize * cin * n, (batch * h * w, ksize * ksize * cin, n, ksize), nbytes))
+        stats_on = (len(rest) > 2 and rest[2] is not None) or kw.get("stats") is not None
+        recs.append((s, e, 2.0 * batch * h * w * ksize * ksize * cin * n, (batch * h * w, ksize * ksize * cin, n, ksize), nbytes,
+                     {"batch": batch, "h": h, "w": w, "cin": cin, "flags": flags, "ksplit": kw.get("ksplit", 1), "stats": bool(stats_on)}))
 
     orig_stem = ops.conv_s2d_rows
 
@@ -449,7 +451,7 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
         orig_stem(s_hi, s_lo, batch, rows, wout, pitch_px, w, n, c, *rest, **kw)
         e.record()
         m = batch * rows * wout                     # 7x7x3 = 147 algorithmic K (the kernel contracts over the padded 256)
-        recs.append((s, e, 2.0 * m * 147 * n, (m, 147, n, 7), 4.0 * (batch * rows * wout * 4 * 3 + n * 147 + m * n)))
+        recs.append((s, e, 2.0 * m * 147 * n, (m, 147, n, 7), 4.0 * (batch * rows * wout * 4 * 3 + n * 147 + m * n), {}))
 
     ops.conv_bf16x3, ops.conv_s2d_rows = timed, timed_stem
     overlap, eng.overlap_towers = eng.overlap_towers, False      # per-kernel times without the text tower competing for SMs
@@ -465,7 +467,7 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
         eng.overlap_towers, eng.comm = overlap, comm
     if dump:
         rows = [{"M": r[3][0], "K": r[3][1], "N": r[3][2], "ksize": r[3][3], "ms": r[0].elapsed_time(r[1]),
-                 "tflops_algorithmic": r[2] / r[0].elapsed_time(r[1]) / 1e9, "gbytes_per_s": r[4] / r[0].elapsed_time(r[1]) / 1e6} for r in recs]
+                 "tflops_algorithmic": r[2] / r[0].elapsed_time(r[1]) / 1e9, "gbytes_per_s": r[4] / r[0].elapsed_time(r[1]) / 1e6, **r[5]} for r in recs]
         with open(dump, "w") as f:
             json.dump(rows, f, indent=0)
     tot_ms = sum(r[0].elapsed_time(r[1]) for r in recs)

@@ -359,7 +359,10 @@ bool conv3x3_halo_pays(int64_t batch, int64_t h, int64_t w, int64_t cin, int64_t
   const HaloPlan pl = plan_halo(batch, h, w, cin, n, 148);
   const double useful = (double)(h * w) / ((double)pl.p.rt_per_img * BM);      // real pixels per 128-row MMA tile
   if (useful < 0.6) return false;
-  return n <= 128;
+  // measured (profiles/r02_halo_sweep.txt, profiles/r02_policy_sweep.txt): the halo path wins 1.2-2.4x where both the output and
+  // the input are narrow (the Branch_2 3x3 convs and their input gradients); wider contractions are faster on CTA pairs, whose
+  // M = 256 instruction halves the MMA issue count and the weight-tile rows per SM
+  return n <= 96 && cin <= 96;
 }
 
 int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w, int64_t cin,
