@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the text tower on the main stream instead of a side stream")
+    ap.add_argument("--no-branch-overlap", action="store_true", help="run the branches of each inception block on one stream")
     ap.add_argument("--overlap-comm", action="store_true", help="reduce the gradients early on the side stream (measured slower, see Engine.attach_comm)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch records of the contraction kernel pass (shape, ms, TFLOP/s) to this JSON file")
     a = ap.parse_args()
@@ -247,7 +248,8 @@ def run_ours(args):
 
     B, train = args.batch, args.mode == "train"
     eng = Engine(model=args.model, batch=B, precision=args.precision, device=local, seed=0, world_size=world,
-                 dropout="rng" if train else "none", overlap_towers=not args.no_overlap, training=train)
+                 dropout="rng" if train else "none", overlap_towers=not args.no_overlap, training=train,
+                 overlap_branches=not args.no_branch_overlap)
     data = SyntheticPosts(num_samples=B * 4, seed=1234 + rank, with_images=args.model != "text", pool_batches=2)
     pool = [data.next_batch(B), data.next_batch(B)]
 
@@ -455,6 +457,7 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
 
     ops.conv_bf16x3, ops.conv_s2d_rows = timed, timed_stem
     overlap, eng.overlap_towers = eng.overlap_towers, False      # per-kernel times without the text tower competing for SMs
+    branches, eng.overlap_branches = eng.overlap_branches, False # ... and without sibling branches running beside the timed kernel
     comm, eng.comm = eng.comm, None
     one = (lambda: eng.train_step(lr)) if train else (lambda: eng.forward(train=False))
     try:
@@ -464,7 +467,7 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
         torch.cuda.synchronize()
     finally:
         ops.conv_bf16x3, ops.conv_s2d_rows = orig, orig_stem
-        eng.overlap_towers, eng.comm = overlap, comm
+        eng.overlap_towers, eng.overlap_branches, eng.comm = overlap, branches, comm
     if dump:
         rows = [{"M": r[3][0], "K": r[3][1], "N": r[3][2], "ksize": r[3][3], "ms": r[0].elapsed_time(r[1]),
                  "tflops_algorithmic": r[2] / r[0].elapsed_time(r[1]) / 1e9, "gbytes_per_s": r[4] / r[0].elapsed_time(r[1]) / 1e6, **r[5]} for r in recs]

@@ -337,7 +337,7 @@ class Engine:
                  rnn_size: int = 1024, fc_size: int = 512, vocab: int = 400001, emb_dim: int = 50, post_size: int = 50,
                  precision: str = "bf16x3", device: int = 0, seed: int = 0, world_size: int = 1, dropout: str = "rng",
                  unbiased_moving_var: bool = False, final_endpoint: str = "Mixed_5c", training: bool = True,
-                 overlap_towers: bool = True):
+                 overlap_towers: bool = True, overlap_branches: bool = True):
         if model not in ("joint", "image", "text"):
             raise ValueError("unknown model %r" % model)
         if precision not in ("bf16x3", "fp32"):
@@ -353,6 +353,10 @@ class Engine:
         self.precision, self.world_size, self.dropout, self.unbiased_moving_var = precision, world_size, dropout, unbiased_moving_var
         self.training = training
         self.overlap_towers, self._side = overlap_towers, None
+        # the branches of an inception block are independent until the concat: run them on sibling streams so that the HBM-bound
+        # kernels of one branch (pool, BN apply) fill the machine while another branch's contraction holds the tensor pipe
+        self.overlap_branches, self._branch = overlap_branches, None
+        self.blocks = {}                # first node of an inception block (its pool) -> (pool, u1, u2, u3, u4, group or None)
         self.comm, self.first_frozen_boundary, self.overlap_comm = None, None, False
         self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
         self.device = torch.device("cuda", device)
@@ -477,10 +481,12 @@ class Engine:
                 self.nodes += [pool, u1, u2, u3, u4]
                 if u1.trainable:      # backward reaches `pool` last within the block: every trainable weight gradient is final after it
                     self.first_frozen_boundary = pool
+                grp = None
                 if tr and self.split and self.group_bn_bwd:
                     grp = BlockBwdGroup(self, [(u4, 0), (u3, 0), (u2, 0), (u1, 0)])
                     self.nodes.append(grp); self.groups.append(grp)
                     self.dz_elems = max(self.dz_elems, grp.elems // 2)
+                self.blocks[pool] = (pool, u1, u2, u3, u4, grp)
                 act, dact, c = vO, View(dOUT) if tr else None, ctot
                 producers = [(u1, 0, 0), (u2, 0, c0), (u3, 0, c0 + c1b), (u4, 0, c0 + c1b + c2b)]
         self.tower_out, self.d_tower_out, self.tower_c, self.tower_h = act, dact, c, h
@@ -781,6 +787,79 @@ class Engine:
         return View(self.logits, self.nb_emotions, 0)
 
     # -- forward ---------------------------------------------------------------------------------------------
+    # -- branch streams: the four branches of an inception block only meet at the concat (image_model/inception_v1.py:83-96) -----
+    def _branch_streams(self):
+        if self._branch is None:
+            self._branch = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(2)]
+        return self._branch
+
+    def _run_nodes_fwd(self, train: bool):
+        concurrent = self.overlap_branches and self.split
+        skip = set()
+        for node in self.nodes:
+            if node in skip:
+                continue
+            blk = self.blocks.get(node) if concurrent else None
+            if blk is None:
+                node.fwd(train)
+                continue
+            pool, u1, u2, u3, u4, grp = blk
+            skip.update((u1, u2, u3, u4))
+            cur = torch.cuda.current_stream()
+            sB, sC = self._branch_streams()
+            ev_in = torch.cuda.Event(); ev_in.record(cur)
+            with torch.cuda.stream(sB):             # Branch_3: 3x3/1 max pool -> 1x1 conv
+                sB.wait_event(ev_in)
+                pool.fwd(train); u4.fwd(train)
+                evB = torch.cuda.Event(); evB.record(sB)
+            u1.fwd(train)                           # Branch_0 and the two reduce convs (one fused contraction)
+            ev1 = torch.cuda.Event(); ev1.record(cur)
+            with torch.cuda.stream(sC):             # Branch_2 3x3
+                sC.wait_event(ev1)
+                u3.fwd(train)
+                evC = torch.cuda.Event(); evC.record(sC)
+            u2.fwd(train)                           # Branch_1 3x3
+            cur.wait_event(evB); cur.wait_event(evC)
+
+    def _run_nodes_bwd(self):
+        concurrent = self.overlap_branches and self.split
+        order = list(reversed(self.nodes))
+        by_last = {}
+        if concurrent:
+            for blk in self.blocks.values():
+                pool, u1, u2, u3, u4, grp = blk
+                # only blocks whose units own their dZ region (grouped BN backward) and do not share the weight-gradient scratch
+                if grp is not None and grp.enabled and not u1.trainable:
+                    by_last[grp] = blk
+        skip = set()
+        for node in order:
+            if node not in skip:
+                blk = by_last.get(node)
+                if blk is None:
+                    node.bwd()
+                else:
+                    pool, u1, u2, u3, u4, grp = blk
+                    skip.update((pool, u1, u2, u3, u4))
+                    grp.bwd()                           # BN/ReLU backward of the four leaf segments (one reduce + one apply launch)
+                    cur = torch.cuda.current_stream()
+                    sB, sC = self._branch_streams()
+                    ev = torch.cuda.Event(); ev.record(cur)
+                    with torch.cuda.stream(sB):
+                        sB.wait_event(ev)
+                        u4.bwd()                        # -> dP
+                        evB = torch.cuda.Event(); evB.record(sB)
+                    with torch.cuda.stream(sC):
+                        sC.wait_event(ev)
+                        u3.bwd()                        # -> dT[c1a:]
+                        evC = torch.cuda.Event(); evC.record(sC)
+                    u2.bwd()                            # -> dT[:c1a]
+                    cur.wait_event(evC)
+                    u1.bwd()                            # BN backward of the reduce segment, then the fused input gradient (overwrites dX)
+                    cur.wait_event(evB)
+                    pool.bwd()                          # accumulates onto dX: after u1
+            if node is self.first_frozen_boundary and self.comm is not None and self.overlap_comm:
+                self._reduce_early()          # Mixed_5c / Logits / head (and, stream-ordered, the text tower) are final
+
     # -- two-stream schedule: the text tower is independent of the image tower between the inputs and the head, and its
     # kernels (one small GEMM + gate kernel per time step) leave most of the machine idle - run it on a side stream
     def _fork(self):
@@ -799,8 +878,7 @@ class Engine:
             with self._fork():
                 self.text_fwd(train)
         if self.has_image:
-            for node in self.nodes:
-                node.fwd(train)
+            self._run_nodes_fwd(train)
             mask = None
             if train and self.dropout != "none":
                 if self.dropout == "rng":
@@ -910,10 +988,7 @@ class Engine:
             mask = self.drop_mask if self.dropout != "none" else None
             hw = self.tower_h * self.tower_h
             ops.avgpool_dropout_bwd(View(self.dfeat), B, hw, self.tower_c, mask, 1.0 / DROPOUT_KEEP, self.d_tower_out)
-            for node in reversed(self.nodes):
-                node.bwd()
-                if node is self.first_frozen_boundary and self.comm is not None and self.overlap_comm:
-                    self._reduce_early()          # Mixed_5c / Logits / head (and, stream-ordered, the text tower) are final
+            self._run_nodes_bwd()
         if overlap or (self.comm is not None and self.overlap_comm and self.has_image):
             self._join()
         if self.comm is not None:
