@@ -479,7 +479,8 @@ def kernel_pass(eng, ops, lr, train=True, dump=None):
     # Mixed_4b-4f contractions: 14x14 spatial -> M = batch*196
     m4 = [(r[0].elapsed_time(r[1]), r[2]) for r in recs if r[3][0] == eng.batch * 196]
     m4_ms, m4_fl = sum(x for x, _ in m4), sum(f for _, f in m4)
-    return {"kernel": "conv_bf16x3_kernel (persistent tcgen05 split-bf16 implicit GEMM: 1x1/3x3 conv fwd + dgrad + wgrad, LSTM GEMMs)",
+    return {"kernel": "ds_conv_bf16x3: conv_bf16x3_kernel (persistent tcgen05 split-bf16 implicit GEMM, TMA tiled/im2col staging: 1x1/3x3 conv fwd + "
+                      "dgrad + wgrad, LSTM GEMMs) and conv3x3_halo_kernel (halo-tile staging for the narrow 3x3 layers)",
             "achieved": tot_fl / tot_ms / 1e9, "launches": len(recs), "avg_launch_ms": tot_ms / max(len(recs), 1),
             "kernel_ms_per_step": tot_ms, "algorithmic_gflop_per_step": tot_fl / 1e9,
             "algorithmic_bytes_per_launch": tot_bytes / max(len(recs), 1), "algorithmic_gflop_per_launch": tot_fl / 1e9 / max(len(recs), 1),

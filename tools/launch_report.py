@@ -31,8 +31,8 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print("%-58s %5d %10.1f %5.1f%% %10.1f %8.0f" % (k, n, t, 100 * t / tot, b / 1e6, b / t / 1e3 if t else 0))
 print("total %.1f us over %d launches" % (tot, len(per)))
 if len(sys.argv) > 3 and sys.argv[2] == '--traffic-json':
-    conv = [d for d in per.values() if 'conv_bf16x3' in d['k']]
+    conv = [d for d in per.values() if 'conv_bf16x3' in d['k'] or 'conv3x3_halo' in d['k']]
     tb = sum(d['dram__bytes_read.sum'] + d['dram__bytes_write.sum'] for d in conv)
-    json.dump({"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every conv_bf16x3_kernel launch of one joint "
+    json.dump({"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every conv_bf16x3_kernel / conv3x3_halo_kernel launch of one joint "
                          "training step, batch 256 (%s)" % path, "launches": len(conv), "dram_bytes_total": tb,
                "dram_bytes_per_launch": tb / len(conv)}, open(sys.argv[3], 'w'), indent=1)

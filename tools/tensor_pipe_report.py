@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-layer tensor-pipe utilisation of the Mixed_4 forward contractions from an ncu pass over tools/bench_conv.py:
 
-  ncu --kernel-name regex:conv_bf16x3 --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,\
+  ncu --kernel-name "regex:conv_bf16x3|conv3x3_halo" --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,\
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum \
       --clock-control none --csv --log-file gpurun_out/m4.csv python tools/bench_conv.py --only Mixed_4 --reps 2
 
@@ -37,7 +37,7 @@ for i, n in enumerate(names):
     t = d['gpu__time_duration.sum']
     a = d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
     e = d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed']
-    mode = "cta-pair" if "<0, 1>" in d['k'] or "false, true" in d['k'] else "single"
+    mode = "halo" if "halo" in d['k'] else ("cta-pair" if "<0, 1>" in d['k'] or "false, true" in d['k'] else "single")
     print("%s,%s,%.1f,%.1f,%.1f,%.1f,%.1f" % (n, mode, t, a, e, d['dram__bytes_read.sum'] + d['dram__bytes_write.sum'], d['lts__t_bytes.sum']))
     tw += a * t
     tt += t

@@ -373,13 +373,18 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
         if (do_stats) {
           // column `lane` of the staged tile over this warp's 32 rows (bank-conflict free: a row's 128 bytes span all banks)
-          float a1 = 0.f, a2 = 0.f;
+          // all 32 loads are issued before the first sum: interleaved, every add would wait out its own load's latency
+          float a1 = 0.f, a2 = 0.f, xs[32];
           const uint32_t cchunk = (uint32_t)lane >> 2, cin4 = ((uint32_t)lane & 3u) << 2;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             const uint32_t row = (uint32_t)(quarter * 32 + rr);
-            float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
-            if (ROW_MODE && (int)row >= p.tile_rows) x = 0.f;          // row mode: rows past the image row hold garbage
+            xs[rr] = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            float x = xs[rr];
+            if (ROW_MODE && quarter * 32 + rr >= p.tile_rows) x = 0.f;          // row mode: rows past the image row hold garbage
             a1 += x;
             a2 = fmaf(x, x, a2);
           }

@@ -251,13 +251,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           bulk_commit();
         }
         if (do_stats) {
-          float a1 = 0.f, a2 = 0.f;
+          // all 32 loads are issued before the first sum: interleaved, every add would wait out its own load's latency
+          float a1 = 0.f, a2 = 0.f, xs[32];
           const uint32_t cchunk = (uint32_t)lane >> 2, cin4 = ((uint32_t)lane & 3u) << 2;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             const uint32_t row = (uint32_t)(quarter * 32 + rr);
-            float x = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
-            if (!((vmask >> rr) & 1u)) x = 0.f;
+            xs[rr] = ld_shared_f32(stg + row * 128u + ((cchunk ^ (row & 7u)) << 4) + cin4);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const float x = ((vmask >> rr) & 1u) ? xs[rr] : 0.f;
             a1 += x;
             a2 = fmaf(x, x, a2);
           }
