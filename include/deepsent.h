@@ -54,6 +54,7 @@ int ds_comm_nccl_version(void);
 #define DS_EPI_RELU 1        /* out = max(out, 0)                        */
 #define DS_EPI_ACCUMULATE 2  /* out += previous contents of C            */
 #define DS_EPI_STATS 4       /* also add per-column sum / sum-of-squares into stats[2*N] (double) */
+#define DS_EPI_SPLIT 8       /* (set internally by ds_conv_bf16x3_split_out) the output is two bf16 planes */
 
 /* tcgen05 TF32 implicit GEMM (TMA-staged smem tiles, TMEM accumulator), stride 1, TF-"SAME":
  *   C[m, n] = epi( sum_{r,s,c} A[pixel(m) + (r-p, s-p), c] * Bt[n, (r*ks+s)*cin + c] )
@@ -88,6 +89,20 @@ int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int6
                    int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
                    float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
                    int ksplit, void* stream);
+/* Inference form of a conv + BN + ReLU site (slim.conv2d with normalizer_fn=batch_norm, is_training=False:
+ * image_model/inception_v1.py:71-247 under the arg scope of slim/nets/inception_utils.py:48-70; the correlation_matrix / evaluate_*
+ * path image_text_model/im_text_rnn_model.py:171-207,342-376): the moving-statistics batch norm is folded into the contraction
+ * epilogue, y = relu(acc * scale[n] + bias[n]) with scale = rsqrt(moving_var + eps), bias = beta - moving_mean * scale
+ * (ds_bn_fold), and y is written straight into the split-bf16 planes of the consumer's buffer (y_hi / y_lo, pixel stride ldy in
+ * bf16 elements; a channel slice of a concat buffer is (ptr + offset, ld = 2 * total channels)) - the fp32 pre-activation is never
+ * stored.  Same contraction, operands and launch policy as ds_conv_bf16x3; flags: DS_EPI_RELU only.
+ * Requirements: those of ds_conv_bf16x3, ldy % 8 == 0, 16-byte aligned y_hi / y_lo. */
+int ds_conv_bf16x3_split_out(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                             int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                             uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, const float* scale, const float* bias, int flags,
+                             void* stream);
+/* scale[c] = rsqrt(var[c] + eps), bias[c] = beta[c] - mean[c] * scale[c]: the folded form of an inference-mode batch norm */
+int ds_bn_fold(const float* mean, const float* var, const float* beta, float eps, int64_t n, float* scale, float* bias, void* stream);
 /* fp32 [rows, cols] <-> split planes */
 int ds_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream);
 int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t rows, int64_t cols, float* out, int64_t ldo,

@@ -113,3 +113,30 @@ def test_exact_on_bf16_operands_and_many_tiles(K):
     c = torch.zeros(b * h * h, cout, device=DEV)
     K.conv_bf16x3(to_split(K, x.view(-1, cin)), b, h, h, cin, 3, fwd, cout, K.View(c))
     close(c, O.conv2d(x.double(), w.double(), 1).reshape(-1, cout), 1e-5, "bf16-exact operands")
+
+
+@pytest.mark.parametrize("b,h,cin,cout,ks", [(3, 14, 32, 64, 3), (2, 28, 96, 32, 3), (2, 14, 144, 288, 3), (5, 14, 24, 64, 3), (300, 1, 64, 48, 1),
+                                             (2, 14, 512, 296, 1), (40, 28, 192, 176, 1)])
+def test_inference_epilogue_writes_split_planes(K, b, h, cin, cout, ks):
+    """ds_conv_bf16x3_split_out: y = relu(conv * scale + bias) written as split-bf16 planes straight into a channel window of a wider
+    buffer (the folded inference BN of the correlation_matrix / evaluate_* path); neighbouring channels stay untouched"""
+    g = gen(31)
+    x = torch.rand(b, h, h, cin, generator=g) * 2 - 1
+    w = torch.randn(ks, ks, cin, cout, generator=g) * 0.1
+    fwd, _ = make_weights(K, w)
+    scale, bias = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.3
+    total, off = cout + 24, 16
+    ybuf = torch.full((b * h * h, 2 * total), 7.0, dtype=torch.bfloat16, device=DEV)
+    Y = K.SView(ybuf)
+    K.conv_bf16x3_split_out(to_split(K, x.view(-1, cin)), b, h, h, cin, ks, fwd, cout, Y.slice(off, cout), scale.to(DEV), bias.to(DEV))
+    ref = F.relu(O.conv2d(x.double(), w.double(), 1).reshape(-1, cout) * scale.double() + bias.double())
+    got = Y.slice(off, cout).torch()
+    close(got, ref, 1e-4, "split-out epilogue")
+    full = ybuf.float().cpu()
+    untouched = torch.ones(2 * total, dtype=torch.bool)
+    untouched[off:off + cout] = False
+    untouched[total + off:total + off + cout] = False
+    assert bool((full[:, untouched] == 7.0).all())
+    # 16 significant bits: |lo| stays within half a bf16 ulp of hi
+    hi, lo = full[:, off:off + cout], full[:, total + off:total + off + cout]
+    assert float((lo.abs() - hi.abs() * 2.0 ** -8).max()) <= 1e-30

@@ -41,7 +41,8 @@ bool conv3x3_halo_fits(int64_t batch, int64_t h, int64_t w, int64_t cin, int64_t
 bool conv3x3_halo_pays(int64_t batch, int64_t h, int64_t w, int64_t cin, int64_t n);
 int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w, int64_t cin,
                         const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n, float* c, int64_t ldc,
-                        const float* scale, const float* bias, double* stats, int flags, void* stream);
+                        const float* scale, const float* bias, double* stats, int flags, void* stream,
+                        uint16_t* y_hi = nullptr, uint16_t* y_lo = nullptr, int64_t ldy = 0);
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float to_tf32(float x) {

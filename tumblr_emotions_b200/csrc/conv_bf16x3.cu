@@ -90,7 +90,7 @@ template <bool ROW_MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                   const __grid_constant__ CUtensorMap tmC, const Params p) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -119,7 +119,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmC);
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmC); prefetch_tmap(&tmC2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -360,6 +360,33 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           }
         }
         named_bar_sync(1, 128);                        // staging tile free (leader's wait above) ...
+        if (!ROW_MODE && (p.flags & DS_EPI_SPLIT)) {
+          // inference epilogue: the activation goes out as two bf16 planes (hi | lo), 64-byte rows, two dense staging halves
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t h0, l0, h1, l1;
+            ds::split_bf16(v[2 * j], h0, l0);
+            ds::split_bf16(v[2 * j + 1], h1, l1);
+            hh[j] = h0 | (h1 << 16);
+            ll[j] = l0 | (l1 << 16);
+          }
+          const uint32_t hrow = stg + (uint32_t)r * 64u, lrow = hrow + STG_BYTES / 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_shared_v4_u32(hrow + 16u * j, hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+            st_shared_v4_u32(lrow + 16u * j, ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_2d(&tmC, stg, col0, (int32_t)m0);
+            tma_store_2d(&tmC2, stg + STG_BYTES / 2, col0, (int32_t)m0);
+            bulk_commit();
+          }
+          ++chunk_it;
+          continue;
+        }
         const uint32_t srow = stg + (uint32_t)r * 128u;
 #pragma unroll
         for (int j = 0; j < 8; ++j)                    // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
@@ -439,22 +466,30 @@ int pick_bn(int64_t row_tiles, int64_t n, int ksplit, int workers) {
 
 }  // namespace
 
-extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
-                              int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
-                              float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
-                              int ksplit, void* stream) {
+// common launcher: fp32 output (c, ldc) or, with y_hi != NULL, the split-plane inference epilogue (DS_EPI_SPLIT)
+static int conv_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                       int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                       float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
+                       int ksplit, void* stream, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy) {
   DS_REQUIRE(ds::g_encode_tiled && ds::g_encode_im2col, "ds_init() has not been called");
   DS_REQUIRE(ksize == 1 || ksize == 3, "ds_conv_bf16x3 supports 1x1 and 3x3 filters");
   DS_REQUIRE((ksize == 1 || cin % 8 == 0) && n % 4 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "alignment (see deepsent.h)");
   DS_REQUIRE((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)bt_hi | (uintptr_t)bt_lo | (uintptr_t)c) & 15) == 0, "16-byte aligned bases");
   DS_REQUIRE(!(flags & DS_EPI_STATS) || stats != nullptr, "DS_EPI_STATS needs a stats buffer");
+  const bool split_out = y_hi != nullptr;
+  if (split_out) {
+    DS_REQUIRE(y_lo != nullptr && ldy % 8 == 0 && (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0, "split output: ldy % 8 == 0, 16-byte aligned planes");
+    DS_REQUIRE(!(flags & ~DS_EPI_RELU) && ksplit <= 1, "split output supports the ReLU flag only");
+    flags |= DS_EPI_SPLIT;
+  }
   const int64_t M = batch * h * w;
   if (M == 0 || n == 0) return 0;
   // 3x3: the halo-tile kernel (conv_halo.cu) stages each activation tile once for all nine taps; it takes the launches whose
   // im2col form is bound by operand row requests (dev knob 11: 1 forces the im2col path, 2 forces the halo path where it fits)
   if (ksize == 3 && ksplit <= 1 && ds::g_debug[11] != 1 &&
       (ds::g_debug[11] == 2 ? ds::conv3x3_halo_fits(batch, h, w, cin, n) : ds::conv3x3_halo_pays(batch, h, w, cin, n)))
-    return ds::conv3x3_halo_launch(a_hi, a_lo, lda, batch, h, w, cin, bt_hi, bt_lo, ldb, n, c, ldc, scale, bias, stats, flags, stream);
+    return ds::conv3x3_halo_launch(a_hi, a_lo, lda, batch, h, w, cin, bt_hi, bt_lo, ldb, n, c, ldc, scale, bias, stats, flags, stream,
+                                   y_hi, y_lo, ldy);
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   Params p;
   p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags;
@@ -484,7 +519,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   p.row_mode = 0; p.tile_rows = pair ? 2 * BM : BM; p.rows_per_img = 0; p.band_rows = 0;
   const int64_t ktot = (int64_t)ksize * ksize * cin;
 
-  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC, tmC2;
   int r = 0;
   for (int plane = 0; plane < 2 && !r; ++plane) {
     CUtensorMap* tm = plane ? &tmAl : &tmAh;
@@ -498,7 +533,13 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   if (!r) r = ds::make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)ktot, (uint64_t)ldb, KC, (uint32_t)b_rows);
   if (r) return ds::fail("cuTensorMapEncode(B) failed: CUresult %d (n=%lld ktot=%lld ldb=%lld bn=%d)", r, (long long)n, (long long)ktot, (long long)ldb, p.bn);
 
-  r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (split_out) {
+    r = ds::make_tmap_2d_bf16_plain(&tmC, y_hi, (uint64_t)M, (uint64_t)n, (uint64_t)ldy, 32, BM);
+    if (!r) r = ds::make_tmap_2d_bf16_plain(&tmC2, y_lo, (uint64_t)M, (uint64_t)n, (uint64_t)ldy, 32, BM);
+  } else {
+    r = ds::make_tmap_2d(&tmC, c, (uint64_t)M, (uint64_t)n, (uint64_t)ldc, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    tmC2 = tmC;
+  }
   if (r) return ds::fail("cuTensorMapEncode(C) failed: CUresult %d (M=%lld n=%lld ldc=%lld)", r, (long long)M, (long long)n, (long long)ldc);
 
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_rows * 128;
@@ -533,7 +574,7 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     ++ds::g_debug[15];
-    DS_CUDA(cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<false, true>, tmAh, tmAl, tmBh, tmBl, tmC, p));
+    DS_CUDA(cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<false, true>, tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p));
     return 0;
   }
   // a CTA must keep the same column tile for all its tiles (register-resident batch-norm partial sums): with tiles
@@ -541,9 +582,27 @@ extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
-  conv_bf16x3_kernel<false, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<false, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
   DS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ds_conv_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                              int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                              float* c, int64_t ldc, const float* scale, const float* bias, double* stats, int flags,
+                              int ksplit, void* stream) {
+  DS_REQUIRE(!(flags & DS_EPI_SPLIT), "DS_EPI_SPLIT is set by ds_conv_bf16x3_split_out");
+  return conv_launch(a_hi, a_lo, lda, batch, h, w, cin, ksize, bt_hi, bt_lo, ldb, n, c, ldc, scale, bias, stats, flags, ksplit, stream,
+                     nullptr, nullptr, 0);
+}
+
+extern "C" int ds_conv_bf16x3_split_out(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w,
+                                        int64_t cin, int ksize, const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n,
+                                        uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, const float* scale, const float* bias, int flags,
+                                        void* stream) {
+  DS_REQUIRE(y_hi != nullptr && y_lo != nullptr, "output planes are NULL");
+  return conv_launch(a_hi, a_lo, lda, batch, h, w, cin, ksize, bt_hi, bt_lo, ldb, n, nullptr, 4, scale, bias, nullptr, flags, 1, stream,
+                     y_hi, y_lo, ldy);
 }
 
 // Space-to-depth formulation of the 7x7 / stride-2 stem conv (image_model/inception_v1.py:63): with 2x2 pixel blocks folded into
@@ -606,7 +665,7 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   if (smem < 120 * 1024) smem = 120 * 1024;
   DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t grid = std::min<int64_t>(p.tiles, sms);
-  conv_bf16x3_kernel<true, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv_bf16x3_kernel<true, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -60,7 +60,7 @@ struct HParams {
 __global__ void __launch_bounds__(THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                    const __grid_constant__ CUtensorMap tmC, const HParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const HParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -83,7 +83,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmC);
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmC); prefetch_tmap(&tmC2);
     for (int s = 0; s < MAX_SA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < MAX_SB; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
     mbar_init(bres_bar, 1);
@@ -238,6 +238,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           }
         }
         named_bar_sync(1, 128);
+        if (p.flags & DS_EPI_SPLIT) {
+          // inference epilogue: the activation goes out as two bf16 planes (hi | lo), 64-byte rows, two dense staging halves
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t h0, l0, h1, l1;
+            ds::split_bf16(v[2 * j], h0, l0);
+            ds::split_bf16(v[2 * j + 1], h1, l1);
+            hh[j] = h0 | (h1 << 16);
+            ll[j] = l0 | (l1 << 16);
+          }
+          const uint32_t hrow = stg + (uint32_t)r * 64u, lrow = hrow + STG_BYTES / 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_shared_v4_u32(hrow + 16u * j, hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+            st_shared_v4_u32(lrow + 16u * j, ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_4d(&tmC, stg, col0, 0, h0, img);
+            tma_store_4d(&tmC2, stg + STG_BYTES / 2, col0, 0, h0, img);
+            bulk_commit();
+          }
+          ++chunk_it;
+          continue;
+        }
         const uint32_t srow = stg + (uint32_t)r * 128u;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -371,7 +398,8 @@ bool conv3x3_halo_pays(int64_t batch, int64_t h, int64_t w, int64_t cin, int64_t
 
 int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, int64_t batch, int64_t h, int64_t w, int64_t cin,
                         const uint16_t* bt_hi, const uint16_t* bt_lo, int64_t ldb, int64_t n, float* c, int64_t ldc,
-                        const float* scale, const float* bias, double* stats, int flags, void* stream) {
+                        const float* scale, const float* bias, double* stats, int flags, void* stream, uint16_t* y_hi, uint16_t* y_lo,
+                        int64_t ldy) {
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   HaloPlan pl = plan_halo(batch, h, w, cin, n, sms);
   DS_REQUIRE(pl.ok, "problem does not fit the halo-tile kernel");
@@ -379,7 +407,7 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
   p.flags = flags; p.scale = scale; p.bias = bias; p.stats = stats;
   DS_REQUIRE(!((flags & DS_EPI_ACCUMULATE) && (flags & (DS_EPI_RELU | DS_EPI_STATS))), "the accumulate epilogue is an in-L2 add: no ReLU / stats");
 
-  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC, tmC2;
   for (int plane = 0; plane < 2; ++plane) {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)w * lda * 2, (cuuint64_t)h * w * lda * 2};
@@ -393,7 +421,18 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
   int r = make_tmap_2d_bf16(&tmBh, bt_hi, (uint64_t)n, (uint64_t)(9 * cin), (uint64_t)ldb, KC, (uint32_t)p.bn);
   if (!r) r = make_tmap_2d_bf16(&tmBl, bt_lo, (uint64_t)n, (uint64_t)(9 * cin), (uint64_t)ldb, KC, (uint32_t)p.bn);
   if (r) return fail("cuTensorMapEncode(halo B) failed: CUresult %d", r);
-  {
+  if (flags & DS_EPI_SPLIT) {      // inference epilogue: two dense bf16 planes through unswizzled 4-D maps (64-byte rows)
+    for (int plane = 0; plane < 2; ++plane) {
+      cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+      cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)w * ldy * 2, (cuuint64_t)h * w * ldy * 2};
+      cuuint32_t box[4] = {32, (cuuint32_t)p.Wp, (cuuint32_t)p.R, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult cr = g_encode_tiled(plane ? &tmC2 : &tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane ? y_lo : y_hi, dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncode(halo split C) failed: CUresult %d", (int)cr);
+    }
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)ldc * 4, (cuuint64_t)w * ldc * 4, (cuuint64_t)h * w * ldc * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)p.Wp, (cuuint32_t)p.R, 1};
@@ -401,6 +440,7 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
     CUresult cr = g_encode_tiled(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncode(halo C) failed: CUresult %d", (int)cr);
+    tmC2 = tmC;
   }
   size_t smem = pl.smem;
   DS_REQUIRE(smem <= 227 * 1024, "shared-memory budget exceeded");
@@ -413,7 +453,7 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(p.tiles <= grid || grid % p.tiles_n == 0, "a CTA must keep its column tile: grid % column tiles == 0");
-  conv3x3_halo_kernel<<<(unsigned)grid, THREADS, smem, S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, p);
+  conv3x3_halo_kernel<<<(unsigned)grid, THREADS, smem, S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

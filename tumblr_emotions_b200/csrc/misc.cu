@@ -129,6 +129,19 @@ int blocks_for(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_
 
 }  // namespace
 
+namespace {
+// folded inference batch norm: y = x * scale + bias with scale = rsqrt(var + eps), bias = beta - mean * scale
+__global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ beta, float eps,
+                               int64_t n, float* __restrict__ scale, float* __restrict__ bias) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float s = rsqrtf(var[i] + eps);
+    scale[i] = s;
+    bias[i] = beta[i] - mean[i] * s;
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int ds_softmax_xent(const float* logits, int64_t ldl, const int64_t* labels, int64_t batch, int64_t classes, float scale,
@@ -201,6 +214,13 @@ int ds_fill_hyper(float* hyper, float lr_t, float beta1, float beta2, float eps,
 int ds_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream) {
   if (n == 0) return 0;
   adam_kernel<<<blocks_for(n), 256, 0, ds::S(stream)>>>(p, g, m, v, n, hyper);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_fold(const float* mean, const float* var, const float* beta, float eps, int64_t n, float* scale, float* bias, void* stream) {
+  if (n == 0) return 0;
+  bn_fold_kernel<<<(unsigned)ds::cdiv(n, 256), 256, 0, ds::S(stream)>>>(mean, var, beta, eps, n, scale, bias);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -33,7 +33,7 @@ PFN_encodeIm2col g_encode_im2col = nullptr;
 
 extern "C" {
 
-int ds_version(void) { return 100; }
+int ds_version(void) { return 200; }
 
 const char* ds_last_error(void) { return ds::last_error().c_str(); }
 

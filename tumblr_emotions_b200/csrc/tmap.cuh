@@ -58,6 +58,19 @@ static inline int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t r
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// bf16 2-D map for the split-plane epilogue store: box = box_cols x box_rows, dense rows (no swizzle)
+static inline int make_tmap_2d_bf16_plain(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                          uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 static inline int make_tmap_im2col_bf16(CUtensorMap* m, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
                                         uint64_t ld, int ks, int pad, uint32_t chans, uint32_t pixels) {
   cuuint64_t dims[4] = {c, w, h, n};

@@ -129,6 +129,7 @@ class ConvUnit:
         self.mov_mean, self.mov_var = e.moving_mean[o:o + n], e.moving_var[o:o + n]
         self.mean, self.rstd = e.bn_mean[o:o + n], e.bn_rstd[o:o + n]
         self.stats, self.sums = e.stats[2 * o:2 * o + 2 * n], e.sums[2 * o:2 * o + 2 * n]
+        self.inf_scale, self.inf_bias = e.inf_scale[o:o + n], e.inf_bias[o:o + n]
 
     def _apply(self, z, mean, rstd, beta, out, flags):
         if self.split:
@@ -140,6 +141,15 @@ class ConvUnit:
     def fwd(self, train: bool):
         e, B, h = self.eng, self.eng.batch, self.h_in
         Zv = View(self.Z)
+        if (not train and self.tc and e.fold_inference and all(sp is None for sp in self.seg_pool)
+                and (e.fold_inference == 1 or len(self.segs) == 1)):
+            # inference: the moving-statistics BN is folded into the contraction epilogue (scale / bias / ReLU) and the activation
+            # goes straight into the consumer's split planes - no fp32 pre-activation, no BN-apply pass.  The fused sibling 1x1
+            # unit writes two buffers (the concat slice and the reduce buffer): one launch per destination.
+            for (c, n), out in zip(self.segs, self.outs):
+                ops.conv_bf16x3_split_out(self.x, B, h, h, self.cin, self.k, self.w_fwd.rows_slice(c, n), n, out,
+                                          self.inf_scale[c:c + n], self.inf_bias[c:c + n])
+            return
         if self.tc:
             ops.conv_bf16x3(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.N, Zv, stats=self.stats if train else None)
         elif self.stem_tc:
@@ -356,6 +366,7 @@ class Engine:
         # the branches of an inception block are independent until the concat: run them on sibling streams so that the HBM-bound
         # kernels of one branch (pool, BN apply) fill the machine while another branch's contraction holds the tensor pipe
         self.overlap_branches, self._branch = overlap_branches, None
+        self.fold_inference = int(os.environ.get("DS_FOLD_INFERENCE", "2"))      # 0 off, 1 every unit, 2 single-destination units only
         self.blocks = {}                # first node of an inception block (its pool) -> (pool, u1, u2, u3, u4, group or None)
         self.comm, self.first_frozen_boundary, self.overlap_comm = None, None, False
         self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
@@ -545,6 +556,7 @@ class Engine:
             self.moving_mean, self.moving_var = self.new(n), self.new(n)
             self.moving_var.fill_(1.0)
             self.bn_mean, self.bn_rstd = self.new(n), self.new(n)
+            self.inf_scale, self.inf_bias = self.new(n), self.new(n)      # folded inference BN: y = x * scale + bias
             self.stats, self.sums = self.new(2 * n, dtype=torch.float64), self.new(2 * n, dtype=torch.float64)
         self.loss_buf = self.new(4)          # [total, xent, l2_trainable, l2_frozen_const]
 
@@ -878,6 +890,8 @@ class Engine:
             with self._fork():
                 self.text_fwd(train)
         if self.has_image:
+            if not train and self.split and self.fold_inference:      # scale / bias of the folded BN from the current variables
+                ops.bn_fold(self.moving_mean, self.moving_var, self.beta, BN_EPS, self.inf_scale, self.inf_bias)
             self._run_nodes_fwd(train)
             mask = None
             if train and self.dropout != "none":

@@ -112,6 +112,16 @@ def conv_bf16x3(a: SView, batch, h, w, cin, ksize, bt: SView, n, c: View, scale=
                       _p(stats), flags, ksplit, _stream())
 
 
+def conv_bf16x3_split_out(a: SView, batch, h, w, cin, ksize, bt: SView, n, y: SView, scale, bias, flags=EPI_RELU):
+    """inference form: y = relu(conv * scale + bias) written straight into the split planes of `y` (a channel window)"""
+    lib().conv_bf16x3_split_out(a.ptr, a.lo_ptr, a.ld, batch, h, w, cin, ksize, bt.ptr, bt.lo_ptr, bt.ld, n, y.ptr, y.lo_ptr, y.ld,
+                                _p(scale), _p(bias), flags, _stream())
+
+
+def bn_fold(mean, var, beta, eps, scale, bias):
+    lib().bn_fold(_p(mean), _p(var), _p(beta), eps, mean.numel(), _p(scale), _p(bias), _stream())
+
+
 def gemm_bf16x3(a: SView, bt: SView, c: View, k=None, bias=None, flags=0, ksplit=1):
     """C[rows, n] = A[rows, k] x Bt[n, k]^T on the tensor cores (split-bf16 operands)"""
     conv_bf16x3(a, a.rows, 1, 1, k if k is not None else a.cols, 1, bt, bt.rows, c, None, bias, None, flags, ksplit)
