@@ -29,6 +29,31 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     # the error channel works without a device: a failed precondition returns non-zero and sets the message
     with pytest.raises(RuntimeError, match="ds_init"):
         lib.conv_bf16x3(0, 0, 8, 1, 1, 1, 8, 1, 0, 0, 8, 4, 0, 4, 0, 0, 0, 0, 1, 0)
+    # round-2 surface: the collective, the inference epilogue, the launch counter
+    for name in ("ds_comm_unique_id", "ds_comm_init", "ds_allreduce_sum_f32", "ds_comm_destroy", "ds_conv_bf16x3_split_out", "ds_bn_fold",
+                 "ds_launch_count"):
+        assert name in protos, name
+    assert lib.launch_count() == 0
+
+
+def test_development_entry_points_live_only_in_the_dev_library():
+    """include/deepsent_dev.h (launch-policy overrides, hardware probes) is exported by libdeepsent_dev.so and NOT by the product
+    library, which is otherwise the same objects"""
+    import ctypes
+    from tumblr_emotions_b200.build import build
+    from tumblr_emotions_b200._lib import DEV_HEADER, DEV_LIB_PATH, LIB_PATH, DeepSentLib, parse_header
+    build()
+    dev_protos = parse_header(DEV_HEADER)
+    assert set(dev_protos) == {"ds_debug_set", "ds_debug_get", "ds_probe_umma_row_shift", "ds_probe_tma_rate"}
+    product = ctypes.CDLL(LIB_PATH)
+    for name in dev_protos:
+        assert not hasattr(product, name), name
+    dev = DeepSentLib(DEV_LIB_PATH, dev=True)          # resolves every product AND development prototype
+    dev.debug_set(10, 1)
+    assert dev.debug_get(10) == 1
+    dev.debug_set(10, 0)
+    with pytest.raises(RuntimeError, match="bad key"):
+        dev.debug_set(15, 1)                           # the launch counter is not a knob
 
 
 def test_bn_segment_struct_mirrors_the_header():

@@ -13,7 +13,7 @@ Two statements per configuration:
     relative L2 - ~1.5e-2 for the split-bf16 product path's e ~ 2e-4 (measured: 1e-2..2.4e-2 on the Mixed_5c weights, 4e-2 on the
     beta gradients, 3e-3 behind the single FC ReLU; the text tower, which has no gate, sits at 5e-6).  The test measures the flipped
     fraction on the FC layer and reports it beside the error.  After the first Adam step (a sign-like update: +-lr per entry) the
-    trajectories are compared at 2e-2.
+    trajectories are compared at 3e-2 (measured 6e-3 joint, 1e-2 image).
 
 (2) TEACHER-FORCED, eager launches with the same launch policy.  The engine's conv pre-activations (and the FC pre-activation)
     are replaced, layer by layer, by the oracle's, so every gate is the oracle's and forward rounding never reaches the backward
@@ -148,7 +148,7 @@ def _check(rec):
     if bg["n"]:
         assert bg["global"] <= 1e-1 and bg["max"] <= 2e-1, bg
     for s in rec["steps"][1:]:         # after a sign-like Adam step the comparison is between trajectories
-        assert s["logits_rel_l2"] <= (2e-2 if gated else 1e-4) and s["loss_rel"] <= 5e-3, s
+        assert s["logits_rel_l2"] <= (3e-2 if gated else 1e-4) and s["loss_rel"] <= 5e-3, s
         assert s["params_max_abs_diff"] <= 2.1e-3 * (s["step"] + 1)
 
 
