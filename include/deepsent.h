@@ -142,6 +142,20 @@ int ds_bn_finalize_apply_relu_split(const float* z, int64_t ldz, int64_t m, int6
 int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, int64_t ldz, int64_t m, int64_t n,
                                const float* mean, const float* rstd, const float* beta, const double* sums, int64_t sums_ld,
                                uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, float* dbeta, void* stream);
+/* Grouped forward: ds_bn_finalize_apply_relu_split for up to 4 segments with the same row count m in ONE launch - the four units
+ * of an inception block (image_model/inception_v1.py:83-96), each normalising its own conv output into its channel slice of the
+ * block's concat buffer.  `segs` is a HOST array, copied into the launch. */
+typedef struct ds_bn_fwd_segment {
+  const float* z; int64_t ldz;         /* pre-activations [m, n] */
+  int64_t n;                           /* channels of this segment (multiple of 4) */
+  const double* stats; int64_t stats_ld;   /* fp64 batch sums: stats[c], stats[stats_ld + c] */
+  float* moving_mean; float* moving_var;   /* UPDATE_OPS targets (both NULL to skip) */
+  const float* beta;
+  float* mean_out; float* rstd_out;    /* published for the backward pass */
+  uint16_t* y_hi; uint16_t* y_lo; int64_t ldy;   /* split-bf16 output window */
+} ds_bn_fwd_segment;
+int ds_bn_finalize_apply_relu_split_grouped(const ds_bn_fwd_segment* segs, int count, int64_t m, float momentum, float eps, int flags,
+                                            void* stream);
 /* sums[c] += sum_rows dy[row,c] * [y[row,c] > 0] on a max-pooled map: the beta gradient of a frozen conv+BN+ReLU whose only
  * consumer is that max pool (the stem, image_model/inception_v1.py:63-67), without differentiating through the pool.
  * With beta != NULL it also adds sum dy * [y > 0] * (y - beta[c]) into sums[sums_ld + c] (y - beta is xhat where y > 0): both

@@ -76,6 +76,18 @@ def test_bn_segment_struct_mirrors_the_header():
     for (name, is_ptr, ctype), (_, ct) in zip(fields, got):
         assert ct is (ctypes.c_void_p if is_ptr else ctypes.c_int64), (name, ctype)
     assert ctypes.sizeof(ops.BnSegment) == 8 * len(fields)          # all members are 8 bytes wide: no padding either side
+    # the forward twin
+    body = re.search(r"typedef struct ds_bn_fwd_segment \{(.*?)\} ds_bn_fwd_segment;", text, flags=re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if decl:
+            m = re.match(r"(.*?)(\w+)$", decl)
+            names.append((m.group(2), "*" in m.group(1)))
+    assert [n for n, _ in names] == [g[0] for g in ops.BnFwdSegment._fields_]
+    for (name, is_ptr), (_, ct) in zip(names, ops.BnFwdSegment._fields_):
+        assert ct is (ctypes.c_void_p if is_ptr else ctypes.c_int64), name
+    assert ctypes.sizeof(ops.BnFwdSegment) == 8 * len(names)
 
 
 def test_library_sass_uses_tcgen05_tma_and_cta_pairs():

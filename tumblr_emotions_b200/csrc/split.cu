@@ -64,15 +64,13 @@ RowGrid row_grid(int64_t M, int64_t N, int ctas_per_sm, int min_rows = 0) {
 // y = relu((z - mean) * rstd + beta) -> split planes
 // `stats` != NULL fuses ds_bn_finalize: mean / rstd come from the fp64 batch sums (stats[c], stats[stats_ld + c] over M rows),
 // and the first row-CTA publishes them (mean_out / rstd_out, for the backward pass) and updates the moving averages.
-__global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
-                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             float eps, const float* __restrict__ beta,
-                                                             uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
-                                                             int64_t ldy, int flags, int rows_per_cta,
-                                                             const double* __restrict__ stats, int64_t stats_ld, float* mean_out,
-                                                             float* rstd_out, float* moving_mean, float* moving_var, float momentum) {
-  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (col >= N) return;
+__device__ __forceinline__ void bn_apply_split_body(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t col,
+                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                    float eps, const float* __restrict__ beta,
+                                                    uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
+                                                    int64_t ldy, int flags, int rows_per_cta,
+                                                    const double* __restrict__ stats, int64_t stats_ld, float* mean_out,
+                                                    float* rstd_out, float* moving_mean, float* moving_var, float momentum) {
   const bool relu = !(flags & DS_BN_NO_RELU);
   float4 mu, rs;
   if (stats) {
@@ -127,6 +125,47 @@ __global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __rest
         }
         ds::store4_split(y_hi + r * ldy + col, y_lo + r * ldy + col, out);
       }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             float eps, const float* __restrict__ beta,
+                                                             uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
+                                                             int64_t ldy, int flags, int rows_per_cta,
+                                                             const double* __restrict__ stats, int64_t stats_ld, float* mean_out,
+                                                             float* rstd_out, float* moving_mean, float* moving_var, float momentum) {
+  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= N) return;
+  bn_apply_split_body(z, ldz, M, col, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, rows_per_cta, stats, stats_ld, mean_out, rstd_out,
+                      moving_mean, moving_var, momentum);
+}
+
+// Grouped forward: the train-mode finalize + BN + ReLU of up to 4 conv outputs with the same pixel count (the four units of an
+// inception block, each writing its slice of the concat buffer) in ONE launch; the segments' channel groups are laid end to end
+// along blockIdx.x / threadIdx.x, as in the grouped backward below.
+struct BnFwdSegDev {
+  const float* z; int64_t ldz; int64_t n; const double* stats; int64_t stats_ld; float* moving_mean; float* moving_var;
+  const float* beta; float* mean_out; float* rstd_out; uint16_t* y_hi; uint16_t* y_lo; int64_t ldy;
+};
+struct BnFwdSegsDev { BnFwdSegDev s[4]; int count; };
+
+__global__ void __launch_bounds__(256) bn_apply_split_grouped_kernel(const BnFwdSegsDev g, int64_t M, float eps, float momentum, int flags,
+                                                                     int rows_per_cta) {
+  const int64_t cgroup = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t base = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < g.count) {
+      const int64_t ng = g.s[i].n >> 2;
+      if (cgroup >= base && cgroup < base + ng) {
+        const BnFwdSegDev sg = g.s[i];
+        bn_apply_split_body(sg.z, sg.ldz, M, (cgroup - base) * 4, nullptr, nullptr, eps, sg.beta, sg.y_hi, sg.y_lo, sg.ldy, flags, rows_per_cta,
+                            sg.stats, sg.stats_ld, sg.mean_out, sg.rstd_out, sg.moving_mean, sg.moving_var, momentum);
+        return;
+      }
+      base += ng;
     }
   }
 }
@@ -970,6 +1009,31 @@ int ds_bn_finalize_apply_relu_split(const float* z, int64_t ldz, int64_t m, int6
   bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, nullptr, nullptr, eps, beta, y_hi, y_lo, ldy, flags,
                                                              g.rows_per_cta, stats, stats_ld, mean_out, rstd_out, moving_mean, moving_var,
                                                              momentum);
+  DS_LAUNCH_CHECK();
+  return 0;
+}
+
+int ds_bn_finalize_apply_relu_split_grouped(const ds_bn_fwd_segment* segs, int count, int64_t m, float momentum, float eps, int flags,
+                                            void* stream) {
+  if (m == 0 || count == 0) return 0;
+  DS_REQUIRE(count >= 1 && count <= 4, "1..4 segments per grouped launch");
+  BnFwdSegsDev g;
+  g.count = count;
+  int64_t n_total = 0;
+  for (int i = 0; i < count; ++i) {
+    const ds_bn_fwd_segment& a = segs[i];
+    DS_REQUIRE(a.n > 0 && a.n % 4 == 0 && a.ldz % 4 == 0 && a.ldy % 4 == 0, "channel counts must be multiples of 4");
+    DS_REQUIRE(a.stats && a.mean_out && a.rstd_out && a.beta && a.z && a.y_hi && a.y_lo, "missing segment buffers");
+    DS_REQUIRE((a.moving_mean == nullptr) == (a.moving_var == nullptr), "moving_mean / moving_var go together");
+    DS_REQUIRE((((uintptr_t)a.mean_out | (uintptr_t)a.rstd_out | (uintptr_t)a.beta | (uintptr_t)a.z) & 15) == 0, "16-byte alignment");
+    DS_REQUIRE((((uintptr_t)a.y_hi | (uintptr_t)a.y_lo) & 7) == 0, "8-byte aligned planes");
+    g.s[i] = BnFwdSegDev{a.z, a.ldz, a.n, a.stats, a.stats_ld, a.moving_mean, a.moving_var, a.beta, a.mean_out, a.rstd_out, a.y_hi, a.y_lo,
+                         a.ldy};
+    n_total += a.n;
+  }
+  for (int i = count; i < 4; ++i) g.s[i] = g.s[0];
+  const RowGrid rg = row_grid(m, n_total, 16);
+  bn_apply_split_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, eps, momentum, flags, rg.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }

@@ -138,7 +138,14 @@ class ConvUnit:
             ops.bn_apply_relu(z, mean, rstd, BN_EPS, beta, out, flags)
 
     # -- forward -------------------------------------------------------------------------------------------
-    def fwd(self, train: bool):
+    def fwd_segment(self, si: int):
+        """descriptor of output segment `si` for the grouped train-mode finalize + BN + ReLU launch"""
+        (c, n), out = self.segs[si], self.outs[si]
+        return ops.bn_fwd_segment(View(self.Z).slice(c, n), self.stats[c:], self.N, self.mov_mean[c:c + n], self.mov_var[c:c + n],
+                                  self.beta[c:c + n], self.mean[c:c + n], self.rstd[c:c + n], out)
+
+    def fwd(self, train: bool, defer=()):
+        """`defer`: output segments whose BN + ReLU the caller applies later in a grouped launch (train mode, split path)"""
         e, B, h = self.eng, self.eng.batch, self.h_in
         Zv = View(self.Z)
         if (not train and self.tc and e.fold_inference and all(sp is None for sp in self.seg_pool)
@@ -173,9 +180,9 @@ class ConvUnit:
             ops.colstats(Zv, self.stats)
         if train and self.split:      # finalize (mean / rstd / moving averages) fused into the apply launch of each segment
             fl = ops.BN_UNBIASED if e.unbiased_moving_var else 0
-            for (c, n), out, sp in zip(self.segs, self.outs, self.seg_pool):
-                if sp is not None:
-                    continue              # BN + ReLU are applied by the pool node on the pooled pre-activations
+            for si, ((c, n), out, sp) in enumerate(zip(self.segs, self.outs, self.seg_pool)):
+                if sp is not None or si in defer:
+                    continue              # BN + ReLU are applied by the pool node on the pooled pre-activations / by the grouped launch
                 ops.bn_finalize_apply_relu_split(Zv.slice(c, n), self.stats[c:], self.N, self.mov_mean[c:c + n], self.mov_var[c:c + n],
                                                  1.0 - BN_DECAY, BN_EPS, self.beta[c:c + n], self.mean[c:c + n], self.rstd[c:c + n], out, fl)
         elif train:
@@ -383,6 +390,7 @@ class Engine:
         self.bn_cursor, self.bn_index = 0, {}
         self.nodes, self.units, self.groups = [], [], []
         self.group_bn_bwd = os.environ.get("DS_GROUP_BN_BWD", "1") != "0"      # grouped BN-backward launches per inception block
+        self.group_bn_fwd = os.environ.get("DS_GROUP_BN_FWD", "1") != "0"      # grouped BN-forward launch per inception block
         self.adam_t = 0
         self._graph = None
         self._infer_graph = None
@@ -811,27 +819,38 @@ class Engine:
         for node in self.nodes:
             if node in skip:
                 continue
-            blk = self.blocks.get(node) if concurrent else None
+            blk = self.blocks.get(node) if self.split else None
             if blk is None:
                 node.fwd(train)
                 continue
             pool, u1, u2, u3, u4, grp = blk
             skip.update((u1, u2, u3, u4))
-            cur = torch.cuda.current_stream()
-            sB, sC = self._branch_streams()
-            ev_in = torch.cuda.Event(); ev_in.record(cur)
-            with torch.cuda.stream(sB):             # Branch_3: 3x3/1 max pool -> 1x1 conv
-                sB.wait_event(ev_in)
-                pool.fwd(train); u4.fwd(train)
-                evB = torch.cuda.Event(); evB.record(sB)
-            u1.fwd(train)                           # Branch_0 and the two reduce convs (one fused contraction)
-            ev1 = torch.cuda.Event(); ev1.record(cur)
-            with torch.cuda.stream(sC):             # Branch_2 3x3
-                sC.wait_event(ev1)
-                u3.fwd(train)
-                evC = torch.cuda.Event(); evC.record(sC)
-            u2.fwd(train)                           # Branch_1 3x3
-            cur.wait_event(evB); cur.wait_event(evC)
+            # train mode: the BN + ReLU of the block's four concat slices (Branch_0's part of the fused 1x1 unit and the three leaf
+            # convs) run as ONE grouped launch once all four contractions are done - unless the concat only feeds a max pool, whose
+            # node applies BN on the pooled values
+            group = (train and self.group_bn_fwd and all(u.seg_pool[0] is None for u in (u1, u2, u3, u4)))
+            defer = (0,) if group else ()
+            if concurrent:
+                cur = torch.cuda.current_stream()
+                sB, sC = self._branch_streams()
+                ev_in = torch.cuda.Event(); ev_in.record(cur)
+                with torch.cuda.stream(sB):             # Branch_3: 3x3/1 max pool -> 1x1 conv
+                    sB.wait_event(ev_in)
+                    pool.fwd(train); u4.fwd(train, defer)
+                    evB = torch.cuda.Event(); evB.record(sB)
+                u1.fwd(train, defer)                    # Branch_0 and the two reduce convs (one fused contraction)
+                ev1 = torch.cuda.Event(); ev1.record(cur)
+                with torch.cuda.stream(sC):             # Branch_2 3x3
+                    sC.wait_event(ev1)
+                    u3.fwd(train, defer)
+                    evC = torch.cuda.Event(); evC.record(sC)
+                u2.fwd(train, defer)                    # Branch_1 3x3
+                cur.wait_event(evB); cur.wait_event(evC)
+            else:
+                pool.fwd(train); u1.fwd(train, defer); u2.fwd(train, defer); u3.fwd(train, defer); u4.fwd(train, defer)
+            if group:
+                fl = ops.BN_UNBIASED if self.unbiased_moving_var else 0
+                ops.bn_finalize_apply_relu_split_grouped([u.fwd_segment(0) for u in (u1, u2, u3, u4)], u1.M, 1.0 - BN_DECAY, BN_EPS, fl)
 
     def _run_nodes_bwd(self):
         concurrent = self.overlap_branches and self.split

@@ -195,6 +195,23 @@ def bn_relu_bwd_apply_split_grouped(segs, m):
     lib().bn_relu_bwd_apply_split_grouped(addr, len(segs), m, _stream())
 
 
+class BnFwdSegment(ctypes.Structure):
+    """mirror of `ds_bn_fwd_segment` (include/deepsent.h)"""
+    _fields_ = [("z", ctypes.c_void_p), ("ldz", ctypes.c_int64), ("n", ctypes.c_int64), ("stats", ctypes.c_void_p), ("stats_ld", ctypes.c_int64),
+                ("moving_mean", ctypes.c_void_p), ("moving_var", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("mean_out", ctypes.c_void_p),
+                ("rstd_out", ctypes.c_void_p), ("y_hi", ctypes.c_void_p), ("y_lo", ctypes.c_void_p), ("ldy", ctypes.c_int64)]
+
+
+def bn_fwd_segment(z: View, stats, stats_ld, moving_mean, moving_var, beta, mean_out, rstd_out, y: SView) -> BnFwdSegment:
+    return BnFwdSegment(z.ptr, z.ld, z.cols, _p(stats), stats_ld, _p(moving_mean), _p(moving_var), _p(beta), _p(mean_out), _p(rstd_out),
+                        y.ptr, y.lo_ptr, y.ld)
+
+
+def bn_finalize_apply_relu_split_grouped(segs, m, momentum, eps, flags=0):
+    arr = (BnFwdSegment * len(segs))(*segs)
+    lib().bn_finalize_apply_relu_split_grouped(ctypes.addressof(arr), len(segs), m, momentum, eps, flags, _stream())
+
+
 def bn_dbeta(sums, n, dbeta):
     lib().bn_dbeta(_p(sums), n, _p(dbeta), _stream())
 
