@@ -413,8 +413,9 @@ def run_ours(args):
                          "frac_of_sustained_peak": roof["achieved"] / pk["bf16_tflops_sustained"],
                          "frac_issued": roof["issued_tflops"] / peak,
                          "mixed4_frac_issued": (roof["mixed4_issued_tflops"] / peak) if roof["mixed4_issued_tflops"] else None,
-                         "traffic": conv_traffic(),
-                         "traffic_note": "dram bytes per launch from this round's committed ncu pass (profiles/%s_conv_traffic.json); null = not captured" % ROUND})
+                         "traffic": conv_traffic() if (train and args.model == "joint" and B == 256) else None,
+                         "traffic_note": "dram bytes per launch from this round's committed ncu pass over the joint batch-256 training step "
+                                         "(profiles/%s_conv_traffic.json); null = no capture for this workload" % ROUND})
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
