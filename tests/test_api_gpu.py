@@ -201,3 +201,51 @@ def test_analysis_entry_points_on_the_joint_forward(tmp_path):
     with torch.no_grad():
         lg, _ = O.deep_sentiment_forward(images, texts, torch.ones(50, dtype=torch.int64), p, is_training=False)
     assert np.abs(scores[50:] - lg.numpy()).max() <= 1e-3 * np.abs(lg.numpy()).max()
+
+
+def test_real_record_path_end_to_end_with_warm_start(tmp_path, capsys):
+    """The reference's actual deployment shape, no synthetic switch anywhere: TFRecord shards with JPEG payloads, a GloVe file, an
+    ImageNet warm-start export -> train_deep_sentiment -> evaluate_deep_sentiment / correlation_matrix on the validation split.
+    The first training batch's loss is checked against the oracle on the same decoded records and the same warm-started variables."""
+    from image_text_model.im_text_rnn_model import _CONFIG, correlation_matrix, evaluate_deep_sentiment, train_deep_sentiment
+    from tumblr_emotions_b200 import api, tfrecord
+    d = str(tmp_path / "data")
+    tfrecord.write_synthetic_dataset(d, num_train=8, num_valid=8, num_classes=6, vocab_size=61, shards=2, seed=9, with_images=True,
+                                     image_hw=(120, 150))
+    text_dir = tmp_path / "text_model" / "embedding_weights"
+    text_dir.mkdir(parents=True)
+    glove = (np.random.RandomState(2).randn(60, 50) * 0.4).astype(np.float32)
+    with open(str(text_dir / "glove.6B.50d.txt"), "w") as f:
+        for i, v in enumerate(glove):
+            f.write("w%d " % i + " ".join(repr(float(x)) for x in v) + "\n")
+    ck = str(tmp_path / "pretrained")
+    os.makedirs(ck)
+    warm = O.init_params(5, "image", nb_emotions=1001)          # stands in for the ImageNet checkpoint (1001-way Logits, excluded)
+    np.savez(os.path.join(ck, "inception_v1.ckpt.npz"), **{k: v.numpy() for k, v in warm.items()})
+    cfg = dict(_CONFIG, dataset_dir=d, text_dir=str(tmp_path / "text_model"), batch_size=4, cuda_graph=False, seed=0)
+    # what step 0 must compute: a fresh model, warm-started, on the first four records
+    model = api.DeepSentiment(cfg)
+    api.get_init_fn(ck)(model.engine)
+    model.embedding_init()
+    p = {k: v.double() for k, v in model.engine.state_dict().items()}
+    for k in p:
+        if k.startswith("InceptionV1/") and not k.startswith("InceptionV1/Logits"):
+            assert torch.equal(p[k].float(), warm[k]), k
+    b = model.dataset.next_batch(4)
+    with torch.no_grad():
+        logits_ref, _ = O.deep_sentiment_forward(b["images"].double(), b["ids"], b["seq_lens"], p, is_training=False)
+    model.feed(b)
+    model.engine.forward_only()
+    torch.cuda.synchronize()
+    got = model.engine.get_logits().double().cpu()
+    assert float(((got - logits_ref).norm(dim=1) / logits_ref.norm(dim=1)).max()) <= 1e-3
+    del model
+    train_dir = str(tmp_path / "trained")
+    train_deep_sentiment(ck, train_dir, 3, _config=cfg)
+    out = capsys.readouterr().out
+    assert "Finished loading word embedding weights." in out and "Finished training. Last batch loss" in out
+    assert "New learning rate: 0.001" in out and "New learning rate: 0.0003" in out          # epoch = 8 // 4 = 2 steps
+    acc = evaluate_deep_sentiment(train_dir, str(tmp_path / "eval"), "validation", 2, _config=cfg)
+    assert 0.0 <= acc <= 1.0
+    logits, labels = correlation_matrix(2, train_dir, _config=cfg, out_dir=str(tmp_path / "out"))
+    assert logits.shape == (8, 6) and np.isfinite(logits).all() and set(labels.tolist()) <= set(range(6))

@@ -420,3 +420,40 @@ def test_clone_oracle_reduces_to_the_single_replica_step():
     for n in names:
         assert torch.equal(g3[n], g1[n]) and torch.allclose(g2[n], g1[n], rtol=1e-4, atol=1e-7), n
         assert torch.equal(q3[n], q1[n])
+
+
+def _write_glove(text_dir, words):
+    os.makedirs(os.path.join(text_dir, "embedding_weights"), exist_ok=True)
+    vecs = (np.random.RandomState(3).randn(words, 50) * 0.4).astype(np.float32)
+    with open(os.path.join(text_dir, "embedding_weights", "glove.6B.50d.txt"), "w") as f:
+        for i, v in enumerate(vecs):
+            f.write("w%d " % i + " ".join(repr(float(x)) for x in v) + "\n")
+    return vecs
+
+
+def test_real_record_split_with_jpeg_images(tmp_path):
+    """N2 end of the input side: records with a JPEG payload are decoded and pushed through preprocess_for_eval (TF-1.x central crop +
+    legacy bilinear resize, [-1, 1]); fields and dtypes follow the record schema (datasets/convert_to_dataset.py:148-161)"""
+    from PIL import Image
+    import io
+    from tumblr_emotions_b200 import tfrecord as T
+    from tumblr_emotions_b200.data import open_split
+    d = str(tmp_path / "data")
+    T.write_synthetic_dataset(d, num_train=12, num_valid=4, num_classes=6, vocab_size=41, shards=2, seed=5, with_images=True, image_hw=(90, 120))
+    _write_glove(str(tmp_path / "text_model"), 40)
+    cfg = {'text_dir': str(tmp_path / "text_model"), 'emb_dir': 'embedding_weights', 'filename': 'glove.6B.50d.txt'}
+    ds = open_split("train", d, cfg)
+    assert ds.num_samples == 12 and ds.num_classes == 6 and ds.vocab_size == 41
+    b = ds.next_batch(5)
+    assert b["images"].shape == (5, 224, 224, 3) and b["images"].dtype == torch.float32
+    assert float(b["images"].min()) >= -1.0 and float(b["images"].max()) <= 1.0 and float(b["images"].std()) > 0.1
+    assert b["ids"].dtype == torch.int64 and b["post_ids"].tolist() == [0, 1, 2, 3, 4]
+    # the first record, redone by hand: decode, crop dim // 16 on each side, legacy resize, (x - 0.5) * 2
+    first = T.decode_example(next(T.read_records(T.split_files("train", d)[0])))
+    img = np.asarray(Image.open(io.BytesIO(first['image/encoded'])).convert("RGB"), dtype=np.float32) / 255.0
+    h, w = img.shape[:2]
+    crop = torch.from_numpy(img[h // 16:h - h // 16, w // 16:w - w // 16])
+    ref = (T.tf1_resize_bilinear(crop, 224, 224) - 0.5) * 2.0
+    assert torch.equal(b["images"][0], ref)
+    # image-only model: no embedding table is built (image_model/im_model.py:139-164)
+    assert open_split("validation", d, {}, with_text=False).embedding is None

@@ -211,10 +211,21 @@ def read_split_sizes(dataset_dir, photos_subdir='photos') -> Dict[str, int]:
     return out
 
 
+def _synthetic_jpeg(rng, h: int, w: int) -> bytes:
+    """a smooth random RGB picture, JPEG-encoded (the record's 'image/encoded' payload, dataset_utils.py:65-76)"""
+    from PIL import Image
+    yy, xx = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
+    chans = [127.5 + 127.5 * np.sin(2 * np.pi * (rng.rand() * 3 * yy + rng.rand() * 3 * xx + rng.rand())) for _ in range(3)]
+    buf = io.BytesIO()
+    Image.fromarray(np.stack(chans, -1).astype(np.uint8)).save(buf, format="JPEG", quality=92)
+    return buf.getvalue()
+
+
 def write_synthetic_dataset(dataset_dir: str, num_train: int = 1000, num_valid: int = 0, num_classes: int = 15,
-                            vocab_size: int = 400001, shards: int = 5, seed: int = 0, post_size: int = POST_SIZE):
+                            vocab_size: int = 400001, shards: int = 5, seed: int = 0, post_size: int = POST_SIZE,
+                            with_images: bool = False, image_hw=(300, 400)):
     """Config 1 of BASELINE.json: synthetic (token_ids, label) records in the reference schema, 5 shards per split
-    (convert_images_tfrecords.py:49), no image payload."""
+    (convert_images_tfrecords.py:49); with_images=True adds a JPEG payload per record (else none: the text-only configuration)."""
     os.makedirs(os.path.join(dataset_dir, 'tfrecords'), exist_ok=True)
     os.makedirs(os.path.join(dataset_dir, 'photos'), exist_ok=True)
     rng = np.random.RandomState(seed)
@@ -228,7 +239,8 @@ def write_synthetic_dataset(dataset_dir: str, num_train: int = 1000, num_valid: 
                 sl = int(rng.randint(1, post_size + 1))
                 ids = np.full(post_size, vocab_size - 1, dtype=np.int64)
                 ids[:sl] = rng.randint(0, vocab_size - 1, sl)
-                payloads.append(encode_example({'image/encoded': b'', 'image/format': b'jpg', 'image/class/label': int(rng.randint(num_classes)),
+                jpeg = _synthetic_jpeg(rng, image_hw[0] + int(rng.randint(0, 40)), image_hw[1] + int(rng.randint(0, 40))) if with_images else b''
+                payloads.append(encode_example({'image/encoded': jpeg, 'image/format': b'jpg', 'image/class/label': int(rng.randint(num_classes)),
                                                 'image/height': 0, 'image/width': 0, 'text': ids, 'seq_len': sl, 'post_id': pid,
                                                 'day': int(rng.randint(7))}))
                 pid += 1
