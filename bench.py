@@ -206,7 +206,10 @@ def workload_config(args, world, cpu_arm=False):
     else:
         cfg["precision"] = ("split-bf16 (hi+lo) operands, 3 tcgen05 kind::f16 passes per product, fp32 accumulate/storage"
                             if args.precision == "bf16x3" else "fp32 SIMT")
-        cfg["l2_policy"] = "per-step working set (>10 GB of activations at batch 256) exceeds the 126 MB L2; no flush needed"
+        cfg["l2_policy"] = ("inputs larger than L2, no flush: the step's working set is ~0.2 GB at batch 32 (activations and saved gates "
+                            "~90 MB, parameters + gradients + Adam state ~110 MB) against the 126 MB L2" if args.model == "text" else
+                            "inputs larger than L2, no flush: the step's working set (>10 GB of activations at batch 256, >5 GB at "
+                            "128) exceeds the 126 MB L2 many times over")
         if args.mode == "infer":
             cfg["posts_total"] = 100000
     return cfg
@@ -393,7 +396,8 @@ def run_ours(args):
         conv_flop = CONV_FLOP_TRAIN_PER_SAMPLE if train else CONV_FLOP_FWD_PER_SAMPLE
         line = {"metric": metric_name(args), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x3" if args.precision == "bf16x3" else "f32", "data": "synthetic", "config": workload_config(args, world),
+                "dtype": "bf16x3" if args.precision == "bf16x3" else "f32", "data": "synthetic",
+                "config": dict(workload_config(args, world), dependent_launch=eng.dependent_launch),
                 "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),

@@ -31,6 +31,17 @@ int ds_sm_count(void);
 /* number of kernels this library has launched so far in the process (monotonic; host counter, no synchronisation): the
  * benchmark's `gpu_launches` claim is the difference across one captured step */
 int ds_launch_count(void);
+/* Programmatic dependent launch policy of the calling process (default 0 = every kernel starts when its predecessor in the
+ * stream has completed).  Every kernel of the library waits (griddepcontrol.wait) before its first global-memory access, so
+ * with a bit set the *launch latency and data-independent prologue* of a kernel overlap the tail of its predecessor; results
+ * are identical in every mode.  Measured on B200 (profiles/r02_pdl_sweep.txt): with mode 3 the launch-bound text model
+ * (config 1: 220 dependent launches of ~6 us) gains 12-14 % and the image model 1.5-2.6 %; the joint model, whose towers run
+ * on two streams, loses 1-3 % in every mode (a kernel that waits on an SM holds shared memory the other tower could use), so the
+ * engines choose per model. */
+#define DS_PDL_CONTRACTIONS 1  /* tensor-core kernels may be scheduled before their predecessor has finished */
+#define DS_PDL_ELEMENTWISE 2   /* the same for every other kernel */
+#define DS_PDL_EARLY_RELEASE 4 /* a tensor-core kernel lets its successor in right after its own prologue (else at teardown) */
+int ds_dependent_launch(int mode);
 
 /* ---- data-parallel collective (one process per GPU) --------------------------------------------------
  * The reference's only multi-device precedent is slim/deployment/model_deploy.py: per-clone losses scaled by 1/num_clones

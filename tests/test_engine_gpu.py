@@ -247,3 +247,44 @@ def test_batch_of_one_and_odd_batch():
         torch.cuda.synchronize()
         assert row_rel_l2(eng.get_logits(), logits_ref) <= 1e-3, batch
         assert abs(eng.total_loss() - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
+
+
+@pytest.mark.parametrize("model,mode", [("text", 0), ("text", 3), ("text", 7), ("joint", 1), ("joint", 3), ("joint", 7)])
+def test_results_do_not_depend_on_the_dependent_launch_policy(model, mode, monkeypatch):
+    """ds_dependent_launch: with programmatic dependent launch every kernel may be scheduled before its predecessor has finished and
+    waits (griddepcontrol.wait) before touching global memory.  A missing wait would show up here as a race: two eager steps and
+    two captured steps (programmatic edges inside the CUDA graph, towers and branches on sibling streams) must reproduce the
+    default policy's parameters to the run-to-run rounding of test_graph_replay_equals_eager, and the oracle's logits."""
+    monkeypatch.setenv("DS_PDL", "0")
+    ref, p, bd, mask = make(model, 4, "bf16x3")
+    ref.train_step(1e-3)
+    ref.train_step(1e-3)
+    monkeypatch.setenv("DS_PDL", str(mode))
+    eng, _, _, _ = make(model, 4, "bf16x3")
+    assert eng.dependent_launch == mode
+    eng.train_step(1e-3)
+    eng.train_step(1e-3)
+    cap, _, _, _ = make(model, 4, "bf16x3")
+    cap.capture()
+    cap.load_state_dict(p)
+    cap.adam_m.zero_(); cap.adam_v.zero_(); cap.adam_t = 0
+    cap.train_step_graph(1e-3)
+    cap.train_step_graph(1e-3)
+    torch.cuda.synchronize()
+    for other in (eng, cap):
+        d = (other.params - ref.params).abs()
+        assert float(d.max()) <= 2.1 * 2 * 1e-3 and float(d.mean()) <= 2e-6, (float(d.max()), float(d.mean()))
+        assert abs(other.total_loss() - ref.total_loss()) <= 1e-4 * abs(ref.total_loss())
+    p64 = _to64(p)
+    with torch.no_grad():
+        if model == "text":
+            want = O.text_model_forward(bd["ids"], bd["seq_lens"], p64)
+        else:
+            want, _ = O.deep_sentiment_forward(bd["images"].double(), bd["ids"], bd["seq_lens"], p64, is_training=True, dropout_mask=mask.double())
+    fresh, _, _, _ = make(model, 4, "bf16x3")
+    fresh.zero_step_buffers()
+    fresh.forward(train=True)
+    torch.cuda.synchronize()
+    assert row_rel_l2(fresh.get_logits(), want) <= 1e-3
+    from tumblr_emotions_b200 import ops
+    ops.dependent_launch(0)

@@ -31,9 +31,14 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         lib.conv_bf16x3(0, 0, 8, 1, 1, 1, 8, 1, 0, 0, 8, 4, 0, 4, 0, 0, 0, 0, 1, 0)
     # round-2 surface: the collective, the inference epilogue, the launch counter
     for name in ("ds_comm_unique_id", "ds_comm_init", "ds_allreduce_sum_f32", "ds_comm_destroy", "ds_conv_bf16x3_split_out", "ds_bn_fold",
-                 "ds_launch_count"):
+                 "ds_launch_count", "ds_dependent_launch"):
         assert name in protos, name
     assert lib.launch_count() == 0
+    # launch-overlap policy: a host-side setting, any combination of the three DS_PDL_* bits
+    for mode in (0, 3, 7, 0):
+        lib.dependent_launch(mode)
+    with pytest.raises(RuntimeError, match="DS_PDL"):
+        lib.dependent_launch(8)
 
 
 def test_development_entry_points_live_only_in_the_dev_library():

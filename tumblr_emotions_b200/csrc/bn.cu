@@ -11,6 +11,7 @@ constexpr int RED_ROWS = 256;   // rows reduced per CTA in the column-reduction 
 // each thread owns one float4 column group (cg) and strides over rows; blockDim = (cgs_per_block, row_lanes)
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ z, int64_t ldz, int64_t M, int64_t N,
                                                        double* __restrict__ stats, int rows_per_cta) {
+  ds::pdl_enter();
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t cg = (int64_t)blockIdx.x * cgs + threadIdx.x;
   const int64_t col = cg * 4;
@@ -59,6 +60,7 @@ __device__ __forceinline__ void mean_rstd_from_stats(const double* stats, int64_
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t M, int64_t N, float* moving_mean,
                                    float* moving_var, float momentum, float eps, float* mean_out, float* rstd_out,
                                    int flags) {
+  ds::pdl_enter();
   const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
   float mean, var, rstd;
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        float eps, const float* __restrict__ beta,
                                                        float* __restrict__ y, int64_t ldy, int flags) {
+  ds::pdl_enter();
   const bool use_var = (flags & DS_BN_USE_VAR) != 0;
   const int64_t ncg = N >> 2;
   const int64_t total = M * ncg;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ beta, double* __restrict__ sums, int64_t sums_ld,
                                                             int rows_per_cta) {
+  ds::pdl_enter();
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int64_t M, int64_t N, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ beta,
                                                            const double* __restrict__ sums, int64_t sums_ld, float* dbeta, int flags) {
+  ds::pdl_enter();
   const int64_t ncg = N >> 2;
   const int64_t total = M * ncg;
   const double inv_m = 1.0 / (double)M;
@@ -207,7 +212,7 @@ int ds_colstats(const float* z, int64_t ldz, int64_t m, int64_t n, double* stats
   const unsigned gx = (unsigned)ds::cdiv(n / 4, blk.x);
   const int rows = red_rows(m, gx);
   dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
-  colstats_kernel<<<grid, blk, 0, ds::S(stream)>>>(z, ldz, m, n, stats, rows);
+  ds::launch(colstats_kernel, grid, blk, 0, ds::S(stream), z, ldz, m, n, stats, rows);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -217,7 +222,7 @@ int ds_bn_finalize(const double* stats, int64_t m, int64_t n, float* moving_mean
   DS_REQUIRE(stats && mean_out && rstd_out, "ds_bn_finalize needs stats, mean_out and rstd_out");
   DS_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "moving_mean / moving_var go together");
   if (m == 0 || n == 0) return 0;
-  bn_finalize_kernel<<<(unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream)>>>(stats, m, n, moving_mean, moving_var, momentum, eps, mean_out,
+  ds::launch(bn_finalize_kernel, (unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream), stats, m, n, moving_mean, moving_var, momentum, eps, mean_out,
                                                                            rstd_out, flags);
   DS_LAUNCH_CHECK();
   return 0;
@@ -228,7 +233,7 @@ int ds_bn_apply_relu(const float* z, int64_t ldz, int64_t m, int64_t n, const fl
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "channel counts must be multiples of 4");
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)y) & 15) == 0, "16-byte alignment");
   if (m == 0 || n == 0) return 0;
-  bn_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y, ldy, flags);
+  ds::launch(bn_apply_kernel, elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream), z, ldz, m, n, mean, rstd, eps, beta, y, ldy, flags);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -241,7 +246,7 @@ int ds_bn_relu_bwd_reduce(const float* dy, int64_t lddy, const float* z, int64_t
   const unsigned gx = (unsigned)ds::cdiv(n / 4, blk.x);
   const int rows = red_rows(m, gx);
   dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
-  bn_bwd_reduce_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, rows);
+  ds::launch(bn_bwd_reduce_kernel, grid, blk, 0, ds::S(stream), dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, rows);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -251,7 +256,7 @@ int ds_bn_relu_bwd_apply(const float* dy, int64_t lddy, float* z, int64_t ldz, i
                          void* stream) {
   DS_REQUIRE(n % 4 == 0 && ldz % 4 == 0 && lddy % 4 == 0, "channel counts must be multiples of 4");
   if (m == 0 || n == 0) return 0;
-  bn_bwd_apply_kernel<<<elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums,
+  ds::launch(bn_bwd_apply_kernel, elementwise_blocks(m * (n / 4)), 256, 0, ds::S(stream), dy, lddy, z, ldz, m, n, mean, rstd, beta, sums,
                                                                                sums_ld, dbeta, flags);
   DS_LAUNCH_CHECK();
   return 0;

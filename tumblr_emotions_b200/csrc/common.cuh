@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include "../../include/deepsent.h"
 
 namespace ds {
@@ -35,6 +36,33 @@ extern int g_debug[16];
   } while (0)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ----
+// Every kernel of the library opens with pdl_trigger() (the next kernel of the stream may be scheduled as soon as all CTAs of
+// this one have started) and executes pdl_wait() before its first access to global memory (blocks until the kernels it depends on
+// have completed and their writes are visible), and every launch goes through ds::launch, which allows the overlap.  What
+// overlaps is the launch latency and the data-independent prologue (barrier init, TMEM allocation, tensor-map prefetch) of kernel
+// N+1 with the tail of kernel N; the data dependences are exactly those of a serial stream.  g_pdl (ds_dependent_launch, DS_PDL_*
+// bits of include/deepsent.h) says which launches carry the attribute; without it the two instructions are no-ops.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_as(int pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_as(g_pdl & 2, kern, grid, block, smem, st, std::forward<Args>(args)...);
+}
 
 // halo-tile 3x3 kernel (conv_halo.cu), dispatched from ds_conv_bf16x3
 bool conv3x3_halo_fits(int64_t batch, int64_t h, int64_t w, int64_t cin, int64_t n);

@@ -54,6 +54,7 @@ struct Params {
   const float* bias;
   double* stats;
   int flags;
+  int pdl_early;                 // programmatic dependent launch: let the next kernel in right after the prologue (else at teardown)
   int bn;            // columns per tile (multiple of 16, <= 256)
   int tiles_n;       // column tiles
   int ksplit;        // K splits (grid-strided third tile dimension; epilogue adds atomically when > 1)
@@ -139,6 +140,9 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   __syncthreads();
   if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
+  ds::pdl_wait();
+  if (p.pdl_early) ds::pdl_trigger();
+                // everything above touched only shared / tensor memory; the operands are final from here on
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
@@ -448,6 +452,7 @@ conv_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (!p.pdl_early) ds::pdl_trigger();
   if (PAIR) cluster_sync_all();           // both CTAs are done with the pair's tensor memory and barriers
   if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS); else tmem_dealloc(tmem_base, 2 * ACC_COLS); }
 }
@@ -492,7 +497,7 @@ static int conv_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, 
                                    y_hi, y_lo, ldy);
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   Params p;
-  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags;
+  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = scale; p.bias = bias; p.stats = stats; p.flags = flags; p.pdl_early = (ds::g_pdl & 4) != 0;
   p.ksize = ksize; p.cin = (int)cin; p.cpt = (int)((cin + KC - 1) / KC);
   p.iters = ksize * ksize * p.cpt;
   if (ksplit < 1) ksplit = 1;
@@ -569,10 +574,12 @@ static int conv_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, 
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ds::S(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (ds::g_pdl & 1) ? 2 : 1;
     ++ds::g_debug[15];
     DS_CUDA(cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<false, true>, tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p));
     return 0;
@@ -582,7 +589,7 @@ static int conv_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, 
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.ksplit == 1 && p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(!(flags & DS_EPI_STATS) || p.tiles <= grid || grid % p.tiles_n == 0, "stats epilogue needs grid % column tiles == 0");
-  conv_bf16x3_kernel<false, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
+  ds::launch_as(ds::g_pdl & 1, conv_bf16x3_kernel<false, false>, (unsigned)grid, THREADS, smem, ds::S(stream), tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -622,7 +629,7 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   if (M == 0 || n == 0) return 0;
   const int sms = ds_sm_count() > 0 ? ds_sm_count() : 148;
   Params p;
-  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = nullptr; p.bias = nullptr; p.stats = stats; p.flags = flags;
+  p.M = M; p.N = n; p.ldc = ldc; p.c = c; p.scale = nullptr; p.bias = nullptr; p.stats = stats; p.flags = flags; p.pdl_early = (ds::g_pdl & 4) != 0;
   p.bn = (int)((n + 31) / 32 * 32);
   p.tiles_n = 1; p.ksplit = 1;
   p.ksize = 1; p.cin = KC; p.cpt = 1; p.iters = 4; p.ipz = 4;
@@ -665,7 +672,7 @@ extern "C" int ds_conv_s2d_rows(const uint16_t* s_hi, const uint16_t* s_lo, int6
   if (smem < 120 * 1024) smem = 120 * 1024;
   DS_CUDA(cudaFuncSetAttribute(conv_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t grid = std::min<int64_t>(p.tiles, sms);
-  conv_bf16x3_kernel<true, false><<<(unsigned)grid, THREADS, smem, ds::S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC, p);
+  ds::launch_as(ds::g_pdl & 1, conv_bf16x3_kernel<true, false>, (unsigned)grid, THREADS, smem, ds::S(stream), tmAh, tmAl, tmBh, tmBl, tmC, tmC, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

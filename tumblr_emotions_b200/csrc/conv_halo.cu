@@ -52,6 +52,7 @@ struct HParams {
   int kchunks;          // ceil(9 * cin / 64)
   int nstg;
   int flags;
+  int pdl_early;
   const float* scale;
   const float* bias;
   double* stats;
@@ -94,6 +95,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  ds::pdl_wait();
+  if (p.pdl_early) ds::pdl_trigger();
+                 // the prologue above touched only shared / tensor memory (common.cuh)
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int n0_cta = (int)(blockIdx.x % p.tiles_n) * p.bn;      // the grid is a multiple of tiles_n: a CTA keeps its column tile
 
@@ -322,6 +326,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (!p.pdl_early) ds::pdl_trigger();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
@@ -404,7 +409,7 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
   HaloPlan pl = plan_halo(batch, h, w, cin, n, sms);
   DS_REQUIRE(pl.ok, "problem does not fit the halo-tile kernel");
   HParams& p = pl.p;
-  p.flags = flags; p.scale = scale; p.bias = bias; p.stats = stats;
+  p.flags = flags; p.pdl_early = (g_pdl & 4) != 0; p.scale = scale; p.bias = bias; p.stats = stats;
   DS_REQUIRE(!((flags & DS_EPI_ACCUMULATE) && (flags & (DS_EPI_RELU | DS_EPI_STATS))), "the accumulate epilogue is an in-L2 add: no ReLU / stats");
 
   CUtensorMap tmAh, tmAl, tmBh, tmBl, tmC, tmC2;
@@ -453,7 +458,7 @@ int conv3x3_halo_launch(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
   int64_t grid = std::min<int64_t>(p.tiles, sms);
   if (p.tiles > grid && p.tiles_n <= grid) grid = grid / p.tiles_n * p.tiles_n;
   DS_REQUIRE(p.tiles <= grid || grid % p.tiles_n == 0, "a CTA must keep its column tile: grid % column tiles == 0");
-  conv3x3_halo_kernel<<<(unsigned)grid, THREADS, smem, S(stream)>>>(tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
+  launch_as(g_pdl & 1, conv3x3_halo_kernel, (unsigned)grid, THREADS, smem, S(stream), tmAh, tmAl, tmBh, tmBl, tmC, tmC2, p);
   DS_LAUNCH_CHECK();
   return 0;
 }

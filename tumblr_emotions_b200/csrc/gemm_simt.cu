@@ -41,6 +41,7 @@ template <class ALoad, bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(ALoad A, const float* __restrict__ b, int64_t sbk, int64_t sbn,
                                                         float* __restrict__ c, int64_t ldc, int64_t M, int64_t N, int64_t K,
                                                         int64_t k_per_split, const float* __restrict__ bias, int flags) {
+  ds::pdl_enter();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(ALoad A, const float* __
 
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int64_t rows, int64_t cols,
                                  float* __restrict__ out, int64_t ldout) {
+  ds::pdl_enter();
   __shared__ float tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -126,6 +128,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int
 
 __global__ void repack_kernel(const float* __restrict__ hwio, int kh, int kw, int64_t cin, int64_t cout,
                               float* __restrict__ fwd, float* __restrict__ dgrad, int64_t dgrad_ld, int round_tf32) {
+  ds::pdl_enter();
   const int64_t total = (int64_t)kh * kw * cin * cout;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t co = i % cout; int64_t t = i / cout;
@@ -152,7 +155,7 @@ int launch(ALoad A, bool a_kfast, const float* b, int64_t sbk, int64_t sbn, floa
     if (!(flags & DS_EPI_ACCUMULATE)) DS_CUDA(cudaMemset2DAsync(c, ldc * sizeof(float), 0, N * sizeof(float), M, st));
   }
   dim3 grid((unsigned)ds::cdiv(M, TM), (unsigned)ds::cdiv(N, TN), (unsigned)splits);
-#define DS_GO(AK, BK) gemm_simt_kernel<ALoad, AK, BK><<<grid, 256, 0, st>>>(A, b, sbk, sbn, c, ldc, M, N, K, kps, bias, flags)
+#define DS_GO(AK, BK) ds::launch(gemm_simt_kernel<ALoad, AK, BK>, grid, 256, 0, st, A, b, sbk, sbn, c, ldc, M, N, K, kps, bias, flags)
   if (a_kfast) { if (b_kfast) DS_GO(true, true); else DS_GO(true, false); }
   else { if (b_kfast) DS_GO(false, true); else DS_GO(false, false); }
 #undef DS_GO
@@ -206,7 +209,7 @@ int ds_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t ro
 int ds_transpose(const float* in, int64_t ldin, int64_t rows, int64_t cols, float* out, int64_t ldout, void* stream) {
   if (rows == 0 || cols == 0) return 0;
   dim3 grid((unsigned)ds::cdiv(cols, 32), (unsigned)ds::cdiv(rows, 32));
-  transpose_kernel<<<grid, dim3(32, 8), 0, ds::S(stream)>>>(in, ldin, rows, cols, out, ldout);
+  ds::launch(transpose_kernel, grid, dim3(32, 8), 0, ds::S(stream), in, ldin, rows, cols, out, ldout);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -216,7 +219,7 @@ int ds_repack_conv_weights(const float* hwio, int kh, int kw, int64_t cin, int64
   const int64_t total = (int64_t)kh * kw * cin * cout;
   if (total == 0) return 0;
   const int blocks = (int)std::min<int64_t>(ds::cdiv(total, 256), 148 * 8);
-  repack_kernel<<<blocks, 256, 0, ds::S(stream)>>>(hwio, kh, kw, cin, cout, fwd_ohwi, dgrad_ihwo, dgrad_ld, round_tf32);
+  ds::launch(repack_kernel, blocks, 256, 0, ds::S(stream), hwio, kh, kw, cin, cout, fwd_ohwi, dgrad_ihwo, dgrad_ld, round_tf32);
   DS_LAUNCH_CHECK();
   return 0;
 }

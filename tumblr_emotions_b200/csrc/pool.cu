@@ -8,6 +8,7 @@ namespace {
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t B, int h, int w,
                                                           int c4, int k, int stride, int pad_t, int pad_l, int ho, int wo,
                                                           float* __restrict__ y, int64_t ldy, uint8_t* __restrict__ argmax) {
+  ds::pdl_enter();
   const int64_t total = B * ho * wo * (int64_t)c4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4);
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
                                                           const uint8_t* __restrict__ argmax, int64_t B, int h, int w, int cg_n,
                                                           int pad_t, int pad_l, int ho, int wo,
                                                           float* __restrict__ dx, int64_t lddx, int accumulate) {
+  ds::pdl_enter();
   constexpr int NW = (K + S - 1) / S;
   const int c4 = cg_n * G;                              // float4 groups per pixel
   // one CTA per input row (b, ih): a single 32-bit division per work item instead of a div/mod chain
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_k3s1_walk_kernel(const float*
                                                                     const uint8_t* __restrict__ argmax, int64_t total, int h, int w,
                                                                     int c4, int hseg, int nseg, float* __restrict__ dx, int64_t lddx,
                                                                     int accumulate) {
+  ds::pdl_enter();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = (int)(idx % c4);
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_k3s1_walk_kernel(const float*
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t B, int hw, int c4,
                                                           const float* __restrict__ mask, float inv_keep,
                                                           float* __restrict__ out, int64_t ldo) {
+  ds::pdl_enter();
   const int64_t total = B * c4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4);
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, int64_t ldo, int64_t B, int hw, int c4,
                                                           const float* __restrict__ mask, float inv_keep,
                                                           float* __restrict__ dx, int64_t lddx) {
+  ds::pdl_enter();
   const int64_t total = B * hw * (int64_t)c4;
   const float inv = 1.f / (float)hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -211,6 +216,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 __global__ void dropout_mask_kernel(float* mask, int64_t n, float keep, uint64_t seed, const uint64_t* counter) {
+  ds::pdl_enter();
   const uint64_t ctr = *counter;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t r = splitmix64(splitmix64(seed ^ (ctr * 0xD1342543DE82EF95ull)) + (uint64_t)i);
@@ -218,7 +224,8 @@ __global__ void dropout_mask_kernel(float* mask, int64_t n, float keep, uint64_t
     mask[i] = u < keep ? 1.f : 0.f;
   }
 }
-__global__ void bump_counter_kernel(uint64_t* counter) { *counter += 1; }
+__global__ void bump_counter_kernel(uint64_t* counter) {
+  ds::pdl_enter(); *counter += 1; }
 
 int blocks_for(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(ds::cdiv(total, 256), 148 * 16)); }
 
@@ -232,7 +239,7 @@ int ds_maxpool_fwd(const float* x, int64_t ldx, int64_t batch, int64_t h, int64_
   DS_REQUIRE(k * k < 255, "window too large for uint8 argmax");
   const int64_t total = batch * ho * wo * (c / 4);
   if (total == 0) return 0;
-  maxpool_fwd_kernel<<<blocks_for(total), 256, 0, ds::S(stream)>>>(x, ldx, batch, (int)h, (int)w, (int)(c / 4), k, stride, pad_t,
+  ds::launch(maxpool_fwd_kernel, blocks_for(total), 256, 0, ds::S(stream), x, ldx, batch, (int)h, (int)w, (int)(c / 4), k, stride, pad_t,
                                                                 pad_l, (int)ho, (int)wo, y, ldy, argmax);
   DS_LAUNCH_CHECK();
   return 0;
@@ -251,7 +258,7 @@ int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t
     if (ds::g_debug[9] > 0) hseg = ds::g_debug[9];
     const int nseg = (int)ds::cdiv(h, hseg);
     const int64_t threads = batch * nseg * w * (c / 4);
-    maxpool_bwd_k3s1_walk_kernel<<<(unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream)>>>(dy, lddy, argmax, threads, (int)h, (int)w,
+    ds::launch(maxpool_bwd_k3s1_walk_kernel, (unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream), dy, lddy, argmax, threads, (int)h, (int)w,
                                                                                          (int)(c / 4), hseg, nseg, dx, lddx, accumulate);
     DS_LAUNCH_CHECK();
     return 0;
@@ -262,10 +269,10 @@ int ds_maxpool_bwd(const float* dy, int64_t lddy, const uint8_t* argmax, int64_t
 #define DS_POOL_BWD(KK, SS)                                                                                                           \
   do {                                                                                                                                \
     if (wide)                                                                                                                         \
-      maxpool_bwd_kernel<KK, SS, 2><<<blocks, 128, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 8), pad_t,    \
+      ds::launch(maxpool_bwd_kernel<KK, SS, 2>, blocks, 128, 0, ds::S(stream), dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 8), pad_t,    \
                                                                       pad_l, (int)ho, (int)wo, dx, lddx, accumulate);                 \
     else                                                                                                                              \
-      maxpool_bwd_kernel<KK, SS, 1><<<blocks, 256, 0, ds::S(stream)>>>(dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), pad_t,    \
+      ds::launch(maxpool_bwd_kernel<KK, SS, 1>, blocks, 256, 0, ds::S(stream), dy, lddy, argmax, batch, (int)h, (int)w, (int)(c / 4), pad_t,    \
                                                                       pad_l, (int)ho, (int)wo, dx, lddx, accumulate);                 \
   } while (0)
   if (k == 3 && stride == 1) DS_POOL_BWD(3, 1);
@@ -283,7 +290,7 @@ int ds_avgpool_dropout_fwd(const float* x, int64_t ldx, int64_t batch, int64_t h
                            float* out, int64_t ldo, void* stream) {
   DS_REQUIRE(c % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "channel counts must be multiples of 4");
   if (batch * c == 0) return 0;
-  avgpool_fwd_kernel<<<blocks_for(batch * (c / 4)), 256, 0, ds::S(stream)>>>(x, ldx, batch, (int)hw, (int)(c / 4), mask, inv_keep, out,
+  ds::launch(avgpool_fwd_kernel, blocks_for(batch * (c / 4)), 256, 0, ds::S(stream), x, ldx, batch, (int)hw, (int)(c / 4), mask, inv_keep, out,
                                                                           ldo);
   DS_LAUNCH_CHECK();
   return 0;
@@ -293,7 +300,7 @@ int ds_avgpool_dropout_bwd(const float* dout, int64_t ldo, int64_t batch, int64_
                            float inv_keep, float* dx, int64_t lddx, void* stream) {
   DS_REQUIRE(c % 4 == 0 && lddx % 4 == 0 && ldo % 4 == 0, "channel counts must be multiples of 4");
   if (batch * c == 0) return 0;
-  avgpool_bwd_kernel<<<blocks_for(batch * hw * (c / 4)), 256, 0, ds::S(stream)>>>(dout, ldo, batch, (int)hw, (int)(c / 4), mask,
+  ds::launch(avgpool_bwd_kernel, blocks_for(batch * hw * (c / 4)), 256, 0, ds::S(stream), dout, ldo, batch, (int)hw, (int)(c / 4), mask,
                                                                                inv_keep, dx, lddx);
   DS_LAUNCH_CHECK();
   return 0;
@@ -301,9 +308,9 @@ int ds_avgpool_dropout_bwd(const float* dout, int64_t ldo, int64_t batch, int64_
 
 int ds_dropout_mask(float* mask, int64_t n, float keep, uint64_t seed, uint64_t* counter, void* stream) {
   if (n == 0) return 0;
-  dropout_mask_kernel<<<blocks_for(n), 256, 0, ds::S(stream)>>>(mask, n, keep, seed, counter);
+  ds::launch(dropout_mask_kernel, blocks_for(n), 256, 0, ds::S(stream), mask, n, keep, seed, counter);
   DS_LAUNCH_CHECK();
-  bump_counter_kernel<<<1, 1, 0, ds::S(stream)>>>(counter);
+  ds::launch(bump_counter_kernel, 1, 1, 0, ds::S(stream), counter);
   DS_LAUNCH_CHECK();
   return 0;
 }

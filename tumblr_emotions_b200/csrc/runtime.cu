@@ -26,6 +26,7 @@ int fail(const char* fmt, ...) {
 
 static int g_sm_count = 0;
 int g_debug[16] = {0};
+int g_pdl = 0;
 PFN_encodeTiled g_encode_tiled = nullptr;
 PFN_encodeIm2col g_encode_im2col = nullptr;
 
@@ -59,6 +60,12 @@ int ds_init(int device) {
 int ds_sm_count(void) { return ds::g_sm_count; }
 
 int ds_launch_count(void) { return ds::g_debug[15]; }
+
+int ds_dependent_launch(int mode) {
+  if (mode < 0 || mode > 7) return ds::fail("ds_dependent_launch: mode %d is not a combination of DS_PDL_* bits", mode);
+  ds::g_pdl = mode;
+  return 0;
+}
 
 #ifdef DS_DEV
 // development build only (libdeepsent_dev.so, include/deepsent_dev.h): launch-policy overrides for the tuning tools and the

@@ -16,6 +16,7 @@ int ew_blocks(int64_t total, int per_block = 256) {
 // ---- fp32 <-> split ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int ncg,
                                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ldo) {
+  ds::pdl_enter();
   const int64_t total = rows * ncg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ncg;
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
 
 __global__ void __launch_bounds__(256) merge_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t ldi,
                                                     int64_t rows, int ncg, float* __restrict__ out, int64_t ldo) {
+  ds::pdl_enter();
   const int64_t total = rows * ncg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ncg;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256) bn_apply_split_kernel(const float* __rest
                                                              int64_t ldy, int flags, int rows_per_cta,
                                                              const double* __restrict__ stats, int64_t stats_ld, float* mean_out,
                                                              float* rstd_out, float* moving_mean, float* moving_var, float momentum) {
+  ds::pdl_enter();
   const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (col >= N) return;
   bn_apply_split_body(z, ldz, M, col, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, rows_per_cta, stats, stats_ld, mean_out, rstd_out,
@@ -153,6 +156,7 @@ struct BnFwdSegsDev { BnFwdSegDev s[4]; int count; };
 
 __global__ void __launch_bounds__(256) bn_apply_split_grouped_kernel(const BnFwdSegsDev g, int64_t M, float eps, float momentum, int flags,
                                                                      int rows_per_cta) {
+  ds::pdl_enter();
   const int64_t cgroup = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t base = 0;
 #pragma unroll
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce2_kernel(const float* __rest
                                                              int64_t ldz, int64_t M, int64_t N, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ beta,
                                                              double* __restrict__ sums, int64_t sums_ld, int rows_per_cta) {
+  ds::pdl_enter();
   const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   bn_bwd_reduce2_body(dy, lddy, z, ldz, M, col < N, col, mean, rstd, beta, sums, sums_ld, rows_per_cta);
 }
@@ -256,6 +261,7 @@ __device__ __forceinline__ bool bn_pick_segment(const BnSegsDev& g, int64_t cgro
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce2_grouped_kernel(const BnSegsDev g, int64_t M, int rows_per_cta) {
+  ds::pdl_enter();
   BnSegDev sg = g.s[0];
   int64_t col = 0;
   const bool valid = bn_pick_segment(g, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, sg, col);
@@ -321,12 +327,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(const float* __
                                                                  int64_t sums_ld, uint16_t* __restrict__ dz_hi,
                                                                  uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
                                                                  int rows_per_cta) {
+  ds::pdl_enter();
   const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (col >= N) return;
   bn_bwd_apply_split_body(dy, lddy, z, ldz, M, col, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta, rows_per_cta);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_split_grouped_kernel(const BnSegsDev g, int64_t M, int rows_per_cta) {
+  ds::pdl_enter();
   BnSegDev sg = g.s[0];
   int64_t col = 0;
   if (!bn_pick_segment(g, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, sg, col)) return;
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_split_grouped_kernel(const B
 }
 
 __global__ void bn_dbeta_kernel(const double* __restrict__ sums, int n, float* __restrict__ dbeta) {
+  ds::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dbeta[i] = (float)sums[i];
 }
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(128) maxpool_fwd_split_simd_kernel(const uint1
                                                                      int pad_l, int ho, int wo, uint16_t* __restrict__ y_hi,
                                                                      uint16_t* __restrict__ y_lo, int64_t ldy,
                                                                      uint8_t* __restrict__ argmax) {
+  ds::pdl_enter();
   constexpr uint32_t NEG_INF2 = 0xFF80FF80u;            // packed bf16 -inf: never wins, never ties
   constexpr int KW = K + QW - 1;                         // taps along w loaded per thread (QW > 1 only with stride 1)
   const int64_t b = blockIdx.x / (uint32_t)ho;
@@ -482,6 +492,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_split_k3s1_walk_kernel(const 
                                                                           int64_t ldx, int64_t total, int h, int w, int c8, int hseg, int nseg,
                                                                           uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
                                                                           uint8_t* __restrict__ argmax) {
+  ds::pdl_enter();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = (int)(idx % c8);
@@ -528,6 +539,7 @@ __global__ void __launch_bounds__(128) maxpool_bn_relu_split_kernel(const float*
                                                                     float* moving_var, float momentum,
                                                                     uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
                                                                     uint8_t* __restrict__ argmax, int64_t arg_ld) {
+  ds::pdl_enter();
   const int64_t b = blockIdx.x / (uint32_t)ho;
   const int p = (int)(blockIdx.x - b * ho);
   const uint32_t row_items = (uint32_t)wo * (uint32_t)c4;
@@ -603,6 +615,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_split_kernel(const uint16_t* 
                                                                 int64_t ldx, int64_t B, int hw, int c4,
                                                                 const float* __restrict__ mask, float inv_keep,
                                                                 float* __restrict__ out, int64_t ldo) {
+  ds::pdl_enter();
   const int64_t total = B * c4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4);
@@ -633,6 +646,7 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
                                                                      int64_t ldx, int64_t M, int h, int w, int cin, int ks, int pad,
                                                                      uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
                                                                      int64_t ldo) {
+  ds::pdl_enter();
   __shared__ __align__(16) uint16_t th[64][72], tl[64][72];        // [m][c], rows padded to 144 bytes
   const int tap = blockIdx.z, r = tap / ks, s = tap - r * ks;
   const int64_t m0 = (int64_t)blockIdx.x * 64;
@@ -695,6 +709,7 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
 // One thread per output pixel: 16 channels = two 16-byte stores per plane.
 __global__ void __launch_bounds__(256) s2d_split_kernel(const float* __restrict__ x, int64_t B, int h, int w, int pitch_px,
                                                         uint16_t* __restrict__ s_hi, uint16_t* __restrict__ s_lo) {
+  ds::pdl_enter();
   const int h2 = h >> 1, w2 = w >> 1;
   const int64_t total = B * h2 * (int64_t)pitch_px;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -736,6 +751,7 @@ __global__ void __launch_bounds__(256) masked_colsum_split_kernel(const float* _
                                                                   const uint16_t* __restrict__ y_hi, const uint16_t* __restrict__ y_lo,
                                                                   int64_t ldy, int64_t M, int64_t N, double* __restrict__ sums,
                                                                   int rows_per_cta, const float* __restrict__ beta, int64_t sums_ld) {
+  ds::pdl_enter();
   const int cgs = blockDim.x, rl = blockDim.y;
   const int64_t col = ((int64_t)blockIdx.x * cgs + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
@@ -784,6 +800,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_split_kernel(const f
                                                                          const double* __restrict__ sums, int64_t sums_ld,
                                                                          uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo,
                                                                          int64_t lddz, float* dbeta, int64_t arg_ld) {
+  ds::pdl_enter();
   constexpr int NW = (K + S - 1) / S;
   // column-fixed threads: blockDim = (channel groups, pixel lanes); a thread keeps its 4 channels' parameters in registers
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -868,6 +885,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_bn_apply_k3s2_block_kernel(co
                                                                               int64_t sums_ld, uint16_t* __restrict__ dz_hi,
                                                                               uint16_t* __restrict__ dz_lo, int64_t lddz, float* dbeta,
                                                                               int64_t arg_ld) {
+  ds::pdl_enter();
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;
   if (cg >= c4) return;
   const int col = cg * 4;
@@ -943,6 +961,7 @@ __global__ void repack_split_kernel(const float* __restrict__ hwio, int kh, int 
                                     uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, int64_t fwd_ld, int64_t fwd_rs,
                                     uint16_t* __restrict__ d_hi, uint16_t* __restrict__ d_lo, int64_t dgrad_ld,
                                     int64_t dgrad_tap) {
+  ds::pdl_enter();
   const int64_t total = (int64_t)kh * kw * cin * cout;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t co = i % cout; int64_t t = i / cout;
@@ -968,7 +987,7 @@ extern "C" {
 int ds_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream) {
   DS_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "column counts must be multiples of 4");
   if (rows * cols == 0) return 0;
-  split_kernel<<<ew_blocks(rows * (cols / 4)), 256, 0, ds::S(stream)>>>(x, ldx, rows, (int)(cols / 4), hi, lo, ldo);
+  ds::launch(split_kernel, ew_blocks(rows * (cols / 4)), 256, 0, ds::S(stream), x, ldx, rows, (int)(cols / 4), hi, lo, ldo);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -977,7 +996,7 @@ int ds_merge_bf16(const uint16_t* hi, const uint16_t* lo, int64_t ldi, int64_t r
                   void* stream) {
   DS_REQUIRE(cols % 4 == 0 && ldi % 4 == 0 && ldo % 4 == 0, "column counts must be multiples of 4");
   if (rows * cols == 0) return 0;
-  merge_kernel<<<ew_blocks(rows * (cols / 4)), 256, 0, ds::S(stream)>>>(hi, lo, ldi, rows, (int)(cols / 4), out, ldo);
+  ds::launch(merge_kernel, ew_blocks(rows * (cols / 4)), 256, 0, ds::S(stream), hi, lo, ldi, rows, (int)(cols / 4), out, ldo);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -989,7 +1008,7 @@ int ds_bn_apply_relu_split(const float* z, int64_t ldz, int64_t m, int64_t n, co
   DS_REQUIRE((((uintptr_t)y_hi | (uintptr_t)y_lo) & 7) == 0, "8-byte aligned planes");
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 16);
-  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, g.rows_per_cta,
+  ds::launch(bn_apply_split_kernel, g.grid, g.block, 0, ds::S(stream), z, ldz, m, n, mean, rstd, eps, beta, y_hi, y_lo, ldy, flags, g.rows_per_cta,
                                                              nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f);
   DS_LAUNCH_CHECK();
   return 0;
@@ -1006,7 +1025,7 @@ int ds_bn_finalize_apply_relu_split(const float* z, int64_t ldz, int64_t m, int6
   DS_REQUIRE((((uintptr_t)y_hi | (uintptr_t)y_lo) & 7) == 0, "8-byte aligned planes");
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 16);
-  bn_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(z, ldz, m, n, nullptr, nullptr, eps, beta, y_hi, y_lo, ldy, flags,
+  ds::launch(bn_apply_split_kernel, g.grid, g.block, 0, ds::S(stream), z, ldz, m, n, nullptr, nullptr, eps, beta, y_hi, y_lo, ldy, flags,
                                                              g.rows_per_cta, stats, stats_ld, mean_out, rstd_out, moving_mean, moving_var,
                                                              momentum);
   DS_LAUNCH_CHECK();
@@ -1033,7 +1052,7 @@ int ds_bn_finalize_apply_relu_split_grouped(const ds_bn_fwd_segment* segs, int c
   }
   for (int i = count; i < 4; ++i) g.s[i] = g.s[0];
   const RowGrid rg = row_grid(m, n_total, 16);
-  bn_apply_split_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, eps, momentum, flags, rg.rows_per_cta);
+  ds::launch(bn_apply_split_grouped_kernel, rg.grid, rg.block, 0, ds::S(stream), g, m, eps, momentum, flags, rg.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1045,7 +1064,7 @@ int ds_bn_relu_bwd_apply_split(const float* dy, int64_t lddy, const float* z, in
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dy) & 15) == 0, "16-byte alignment");
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 16);
-  bn_bwd_apply_split_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo,
+  ds::launch(bn_bwd_apply_split_kernel, g.grid, g.block, 0, ds::S(stream), dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo,
                                                                  lddz, dbeta, g.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
@@ -1057,7 +1076,7 @@ int ds_bn_relu_bwd_reduce2(const float* dy, int64_t lddy, const float* z, int64_
   DS_REQUIRE((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)z | (uintptr_t)dy) & 15) == 0, "16-byte alignment");
   if (m == 0 || n == 0) return 0;
   const RowGrid g = row_grid(m, n, 6, 128);
-  bn_bwd_reduce2_kernel<<<g.grid, g.block, 0, ds::S(stream)>>>(dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, g.rows_per_cta);
+  ds::launch(bn_bwd_reduce2_kernel, g.grid, g.block, 0, ds::S(stream), dy, lddy, z, ldz, m, n, mean, rstd, beta, sums, sums_ld, g.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1084,7 +1103,7 @@ int ds_bn_relu_bwd_reduce2_grouped(const ds_bn_segment* segs, int count, int64_t
   int64_t n_total = 0;
   if (int rc = bn_pack_segments(segs, count, g, n_total, false)) return rc;
   const RowGrid rg = row_grid(m, n_total, 6, 128);
-  bn_bwd_reduce2_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, rg.rows_per_cta);
+  ds::launch(bn_bwd_reduce2_grouped_kernel, rg.grid, rg.block, 0, ds::S(stream), g, m, rg.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1095,14 +1114,14 @@ int ds_bn_relu_bwd_apply_split_grouped(const ds_bn_segment* segs, int count, int
   int64_t n_total = 0;
   if (int rc = bn_pack_segments(segs, count, g, n_total, true)) return rc;
   const RowGrid rg = row_grid(m, n_total, 16);
-  bn_bwd_apply_split_grouped_kernel<<<rg.grid, rg.block, 0, ds::S(stream)>>>(g, m, rg.rows_per_cta);
+  ds::launch(bn_bwd_apply_split_grouped_kernel, rg.grid, rg.block, 0, ds::S(stream), g, m, rg.rows_per_cta);
   DS_LAUNCH_CHECK();
   return 0;
 }
 
 int ds_bn_dbeta(const double* sums, int64_t n, float* dbeta, void* stream) {
   if (n == 0) return 0;
-  bn_dbeta_kernel<<<(unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream)>>>(sums, (int)n, dbeta);
+  ds::launch(bn_dbeta_kernel, (unsigned)ds::cdiv(n, 128), 128, 0, ds::S(stream), sums, (int)n, dbeta);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1121,13 +1140,13 @@ int ds_maxpool_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx
     if (ds::g_debug[9] > 0) hseg = ds::g_debug[9];
     const int nseg = (int)ds::cdiv(h, hseg);
     const int64_t threads = batch * nseg * w * (c / 8);
-    maxpool_fwd_split_k3s1_walk_kernel<<<(unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, threads, (int)h, (int)w,
+    ds::launch(maxpool_fwd_split_k3s1_walk_kernel, (unsigned)ds::cdiv(threads, 256), 256, 0, ds::S(stream), x_hi, x_lo, ldx, threads, (int)h, (int)w,
                                                                                                (int)(c / 8), hseg, nseg, y_hi, y_lo, ldy, argmax);
     DS_LAUNCH_CHECK();
     return 0;
   }
 #define DS_GO(KK, QQ)                                                                                                               \
-  maxpool_fwd_split_simd_kernel<KK, QQ><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), \
+  ds::launch(maxpool_fwd_split_simd_kernel<KK, QQ>, (unsigned)(batch * ho), 128, 0, ds::S(stream), x_hi, x_lo, ldx, batch, (int)h, (int)w, (int)(c / 8), \
       stride, pad_t, pad_l, (int)ho, (int)wo, y_hi, y_lo, ldy, argmax)
   if (k == 3 && stride == 1) DS_GO(3, 2);
   else if (k == 3) DS_GO(3, 1);
@@ -1149,7 +1168,7 @@ int ds_maxpool_bn_relu_split(const float* z, int64_t ldz, int64_t batch, int64_t
   if (batch * ho * wo * c == 0) return 0;
   const int64_t m_rows = batch * h * w;
 #define DS_GO(KK)                                                                                                                  \
-  maxpool_bn_relu_split_kernel<KK><<<(unsigned)(batch * ho), 128, 0, ds::S(stream)>>>(z, ldz, batch, (int)h, (int)w, (int)(c / 4), stride, \
+  ds::launch(maxpool_bn_relu_split_kernel<KK>, (unsigned)(batch * ho), 128, 0, ds::S(stream), z, ldz, batch, (int)h, (int)w, (int)(c / 4), stride, \
       pad_t, pad_l, (int)ho, (int)wo, mean, rstd, eps, beta, flags, stats, stats_ld, m_rows, mean_out, rstd_out, moving_mean, moving_var, \
       momentum, y_hi, y_lo, ldy, argmax, arg_ld > 0 ? arg_ld : c)
   if (k == 3) DS_GO(3); else DS_GO(2);
@@ -1162,7 +1181,7 @@ int ds_avgpool_dropout_fwd_split(const uint16_t* x_hi, const uint16_t* x_lo, int
                                  const float* mask, float inv_keep, float* out, int64_t ldo, void* stream) {
   DS_REQUIRE(c % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "channel counts must be multiples of 4");
   if (batch * c == 0) return 0;
-  avgpool_fwd_split_kernel<<<ew_blocks(batch * (c / 4)), 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, batch, (int)hw, (int)(c / 4), mask,
+  ds::launch(avgpool_fwd_split_kernel, ew_blocks(batch * (c / 4)), 256, 0, ds::S(stream), x_hi, x_lo, ldx, batch, (int)hw, (int)(c / 4), mask,
                                                                                 inv_keep, out, ldo);
   DS_LAUNCH_CHECK();
   return 0;
@@ -1178,10 +1197,10 @@ int ds_im2col_transpose_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_
   const bool vec = cin % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 &&
                    (((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)o_hi | (uintptr_t)o_lo) & 15) == 0;
   if (vec)
-    im2col_transpose_split_kernel<true><<<grid, 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
+    ds::launch(im2col_transpose_split_kernel<true>, grid, 256, 0, ds::S(stream), x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
                                                                         o_hi, o_lo, ldo);
   else
-    im2col_transpose_split_kernel<false><<<grid, 256, 0, ds::S(stream)>>>(x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
+    ds::launch(im2col_transpose_split_kernel<false>, grid, 256, 0, ds::S(stream), x_hi, x_lo, ldx, M, (int)h, (int)w, (int)cin, ksize, (ksize - 1) / 2,
                                                                          o_hi, o_lo, ldo);
   DS_LAUNCH_CHECK();
   return 0;
@@ -1192,7 +1211,7 @@ int ds_s2d_split(const float* x, int64_t batch, int64_t h, int64_t w, int64_t pi
   DS_REQUIRE((((uintptr_t)s_hi | (uintptr_t)s_lo) & 15) == 0 && (((uintptr_t)x) & 7) == 0, "aligned buffers");
   const int64_t total = batch * (h / 2) * pitch_px;
   if (total == 0) return 0;
-  s2d_split_kernel<<<ew_blocks(total), 256, 0, ds::S(stream)>>>(x, batch, (int)h, (int)w, (int)pitch_px, s_hi, s_lo);
+  ds::launch(s2d_split_kernel, ew_blocks(total), 256, 0, ds::S(stream), x, batch, (int)h, (int)w, (int)pitch_px, s_hi, s_lo);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1208,7 +1227,7 @@ int ds_masked_colsum_split(const float* dy, int64_t lddy, const uint16_t* y_hi, 
   int64_t rows = ds::cdiv(m, std::max<int64_t>(1, (148 * 24) / gx));
   rows = std::max<int64_t>(256, ds::cdiv(rows, 64) * 64);
   dim3 grid(gx, (unsigned)ds::cdiv(m, rows));
-  masked_colsum_split_kernel<<<grid, blk, 0, ds::S(stream)>>>(dy, lddy, y_hi, y_lo, ldy, m, n, sums, (int)rows, beta, sums_ld);
+  ds::launch(masked_colsum_split_kernel, grid, blk, 0, ds::S(stream), dy, lddy, y_hi, y_lo, ldy, m, n, sums, (int)rows, beta, sums_ld);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -1226,7 +1245,7 @@ int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t*
   const dim3 blk(cgs, std::max(1, 256 / cgs));
   if (k == 3 && stride == 2 && pad_t == 0 && pad_l == 0 && h % 2 == 0 && w % 2 == 0 && ho == h / 2 && wo == w / 2 && ds::g_debug[8] != 1) {
     const dim3 blocks2((unsigned)ds::cdiv(c4, cgs), (unsigned)(batch * ho));
-    maxpool_bwd_bn_apply_k3s2_block_kernel<<<blocks2, blk, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w, c4, mean, rstd,
+    ds::launch(maxpool_bwd_bn_apply_k3s2_block_kernel, blocks2, blk, 0, ds::S(stream), dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w, c4, mean, rstd,
                                                                              beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta,
                                                                              arg_ld > 0 ? arg_ld : c);
     DS_LAUNCH_CHECK();
@@ -1234,7 +1253,7 @@ int ds_maxpool_bwd_bn_apply_split(const float* dyp, int64_t lddy, const uint8_t*
   }
   const dim3 blocks((unsigned)ds::cdiv(c4, cgs), (unsigned)(batch * h));
 #define DS_GO(KK, SS)                                                                                                              \
-  maxpool_bwd_bn_apply_split_kernel<KK, SS><<<blocks, blk, 0, ds::S(stream)>>>(dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
+  ds::launch(maxpool_bwd_bn_apply_split_kernel<KK, SS>, blocks, blk, 0, ds::S(stream), dyp, lddy, argmax, z, ldz, batch, (int)h, (int)w,   \
       (int)(c / 4), pad_t, pad_l, (int)ho, (int)wo, mean, rstd, beta, sums, sums_ld, dz_hi, dz_lo, lddz, dbeta, arg_ld > 0 ? arg_ld : c)
   if (k == 3 && stride == 2) DS_GO(3, 2);
   else if (k == 2 && stride == 2) DS_GO(2, 2);
@@ -1252,7 +1271,7 @@ int ds_repack_conv_weights_split(const float* hwio, int kh, int kw, int64_t cin,
   if (total == 0) return 0;
   DS_REQUIRE((fwd_hi == nullptr) == (fwd_lo == nullptr) && (dgrad_hi == nullptr) == (dgrad_lo == nullptr), "planes go in pairs");
   const int blocks = (int)std::min<int64_t>(ds::cdiv(total, 256), 148 * 8);
-  repack_split_kernel<<<blocks, 256, 0, ds::S(stream)>>>(hwio, kh, kw, cin, cout, fwd_hi, fwd_lo, fwd_ld, fwd_rs > 0 ? fwd_rs : kw * cin,
+  ds::launch(repack_split_kernel, blocks, 256, 0, ds::S(stream), hwio, kh, kw, cin, cout, fwd_hi, fwd_lo, fwd_ld, fwd_rs > 0 ? fwd_rs : kw * cin,
                                                          dgrad_hi, dgrad_lo, dgrad_ld,
                                                          dgrad_tap);
   DS_LAUNCH_CHECK();

@@ -10,6 +10,7 @@ namespace {
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const float* __restrict__ table, int64_t vocab, int dim,
                                                                const int64_t* __restrict__ ids, int64_t B, int64_t T,
                                                                float* __restrict__ out, int64_t ldo, int* __restrict__ oob) {
+  ds::pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __rest
                                                              float forget_bias, float* __restrict__ gates,
                                                              float* __restrict__ c_out, float* __restrict__ h_out,
                                                              uint16_t* __restrict__ h_hi, uint16_t* __restrict__ h_lo, int64_t ldh) {
+  ds::pdl_enter();
   const int n4 = n >> 2;
   const int64_t total = B * n4;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
                                                              float* __restrict__ dh_rec, float* __restrict__ dh_carry,
                                                              float* __restrict__ dc, float* __restrict__ dz,
                                                              uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo, int64_t lddz) {
+  ds::pdl_enter();
   const int n4 = n >> 2;
   const int64_t total = B * n4;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -167,7 +170,7 @@ int ds_embedding_gather(const float* table, int64_t vocab, int64_t dim, const in
   if (batch * steps == 0) return 0;
   const int64_t rows = batch * steps;
   const int blocks = (int)std::min<int64_t>(ds::cdiv(rows, 8), 148 * 16);
-  embedding_gather_kernel<<<blocks, 256, 0, ds::S(stream)>>>(table, vocab, (int)dim, ids, batch, steps, out, ldo, oob_count);
+  ds::launch(embedding_gather_kernel, blocks, 256, 0, ds::S(stream), table, vocab, (int)dim, ids, batch, steps, out, ldo, oob_count);
   DS_LAUNCH_CHECK();
   return 0;
 }
@@ -177,7 +180,7 @@ int ds_lstm_gates_fwd(const float* zh, const float* xw, const float* bias, const
                       float* h_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ldh, void* stream) {
   DS_REQUIRE(n % 4 == 0, "hidden size must be a multiple of 4");
   if (batch * n == 0) return 0;
-  lstm_gates_fwd_kernel<<<blocks_for(batch * (n / 4)), 256, 0, ds::S(stream)>>>(zh, xw, bias, c_prev, h_prev, seq_len, t, batch, (int)n,
+  ds::launch(lstm_gates_fwd_kernel, blocks_for(batch * (n / 4)), 256, 0, ds::S(stream), zh, xw, bias, c_prev, h_prev, seq_len, t, batch, (int)n,
                                                                              forget_bias, gates, c_out, h_out, h_hi, h_lo, ldh);
   DS_LAUNCH_CHECK();
   return 0;
@@ -187,7 +190,7 @@ int ds_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_cu
                       int64_t batch, int64_t n, float* dh_rec, float* dh_carry, float* dc, float* dz, uint16_t* dz_hi, uint16_t* dz_lo, int64_t lddz, void* stream) {
   DS_REQUIRE(n % 4 == 0, "hidden size must be a multiple of 4");
   if (batch * n == 0) return 0;
-  lstm_gates_bwd_kernel<<<blocks_for(batch * (n / 4)), 256, 0, ds::S(stream)>>>(gates, c_prev, c_cur, seq_len, t, batch, (int)n, dh_rec,
+  ds::launch(lstm_gates_bwd_kernel, blocks_for(batch * (n / 4)), 256, 0, ds::S(stream), gates, c_prev, c_cur, seq_len, t, batch, (int)n, dh_rec,
                                                                              dh_carry, dc, dz, dz_hi, dz_lo, lddz);
   DS_LAUNCH_CHECK();
   return 0;

@@ -374,6 +374,13 @@ class Engine:
         # kernels of one branch (pool, BN apply) fill the machine while another branch's contraction holds the tensor pipe
         self.overlap_branches, self._branch = overlap_branches, None
         self.fold_inference = int(os.environ.get("DS_FOLD_INFERENCE", "2"))      # 0 off, 1 every unit, 2 single-destination units only
+        # programmatic dependent launch (ds_dependent_launch): each kernel's launch + prologue overlaps its predecessor's tail.
+        # Measured (profiles/r02_pdl_sweep.txt): the text model - a chain of ~220 short dependent launches - gains 12-14 %, the image
+        # model 1.5-2.6 %; the joint model LOSES 1-3 % in every combination, because kernels of one tower that sit on an SM waiting
+        # for their predecessor hold shared memory the other tower's kernels could have used.  So single-tower engines turn it
+        # on and the joint engine leaves it off.  Process-wide setting, re-asserted at every forward; results are identical.
+        pdl = os.environ.get("DS_PDL", "0" if model == "joint" else "3").split(",")
+        self.dependent_launch, self.dependent_launch_side = int(pdl[0]), int(pdl[-1])
         self.blocks = {}                # first node of an inception block (its pool) -> (pool, u1, u2, u3, u4, group or None)
         self.comm, self.first_frozen_boundary, self.overlap_comm = None, None, False
         self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
@@ -903,11 +910,14 @@ class Engine:
         torch.cuda.current_stream().wait_stream(self._side)
 
     def forward(self, train: bool = True):
+        ops.dependent_launch(self.dependent_launch)      # process-wide policy: (re)assert this engine's choice for its launches
         B = self.batch
         overlap = self.model == "joint" and self.overlap_towers
         if overlap:
             with self._fork():
+                ops.dependent_launch(self.dependent_launch_side)
                 self.text_fwd(train)
+                ops.dependent_launch(self.dependent_launch)
         if self.has_image:
             if not train and self.split and self.fold_inference:      # scale / bias of the folded BN from the current variables
                 ops.bn_fold(self.moving_mean, self.moving_var, self.beta, BN_EPS, self.inf_scale, self.inf_bias)
@@ -1010,7 +1020,9 @@ class Engine:
         overlap = self.model == "joint" and self.overlap_towers
         if overlap:
             with self._fork():
+                ops.dependent_launch(self.dependent_launch_side)
                 self.text_bwd(d_txt)
+                ops.dependent_launch(self.dependent_launch)
         elif self.has_text:
             self.text_bwd(d_txt)
         if self.has_image:

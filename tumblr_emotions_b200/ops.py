@@ -96,6 +96,14 @@ def init(device: int = 0):
     lib().init(device)
 
 
+PDL_CONTRACTIONS, PDL_ELEMENTWISE, PDL_EARLY_RELEASE = 1, 2, 4
+
+
+def dependent_launch(mode: int):
+    """programmatic-dependent-launch policy of the process (include/deepsent.h: DS_PDL_*); results do not depend on it"""
+    lib().dependent_launch(mode)
+
+
 # ---- contractions -------------------------------------------------------------------------------
 def conv_tc(a: View, batch, h, w, cin, ksize, bt, ldb, n, c: View, scale=None, bias=None, stats=None, flags=0):
     if stats is not None:
