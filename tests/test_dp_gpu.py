@@ -136,3 +136,55 @@ def p_start_weight(name):
     if _P0 is None:
         _P0 = {k: v.double() for k, v in _start_params().items()}
     return _P0[name]
+
+
+def _text_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from tumblr_emotions_b200.api import make_comm
+        from tumblr_emotions_b200.engine import Engine
+        eng = Engine(model="text", batch=BATCH, precision="bf16x3", vocab=VOCAB, dropout="none", device=rank, world_size=world)
+        assert eng.dependent_launch == 3        # single-tower engines launch with programmatic dependencies
+        eng.load_state_dict(O.init_params(0, "text", vocab=VOCAB))
+        bd = O.synthetic_batch(BATCH, seed=4321 + rank, vocab=VOCAB, with_images=False)
+        eng.set_batch(None, bd["ids"], bd["seq_lens"], bd["labels"])
+        eng.attach_comm(make_comm(rank, world))
+        eng.capture()
+        eng.train_step_graph(1e-3)
+        eng.train_step_graph(1e-3)
+        torch.cuda.synchronize()
+        torch.save({"logits": eng.get_logits().cpu(), "params": {n: eng.tensor(n).cpu().clone() for n in eng.trainable_names()}},
+                   os.path.join(out_dir, "text_rank%d.pt" % rank))
+        dist.barrier()
+        eng.detach_comm()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_text_model_with_dependent_launches_and_the_collective_in_one_graph(tmp_path):
+    """the text-only engine launches with programmatic dependencies (ds_dependent_launch mode 3); with two ranks the NCCL
+    all-reduce sits in the same captured graph between such kernels.  Two replayed steps must leave both ranks with bit-identical
+    parameters that follow the two-clone oracle's Adam trajectory, and the second step's logits must match the oracle's."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    mp.spawn(_text_worker, args=(WORLD, _free_port(), str(tmp_path)), nprocs=WORLD, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "text_rank%d.pt" % r)) for r in range(WORLD)]
+    p = {k: v.double() for k, v in O.init_params(0, "text", vocab=VOCAB).items()}
+    names = O.trainable_names(p)
+    opt = O.TFAdam(names, p)
+    batches = [O.synthetic_batch(BATCH, seed=4321 + r, vocab=VOCAB, with_images=False) for r in range(WORLD)]
+    O.train_step_clones("text", p, opt, 1e-3, batches)
+    _, _, logits, _ = O.train_step_clones("text", p, opt, 1e-3, batches)
+    dsum = cnt = 0
+    for n in names:
+        assert torch.equal(res[0]["params"][n], res[1]["params"][n]), n
+        d = (res[0]["params"][n].double() - p[n]).abs()
+        assert float(d.max()) <= 2 * 2.1e-3, (n, float(d.max()))
+        dsum, cnt = dsum + float(d.sum()), cnt + d.numel()
+    assert dsum / cnt <= 2e-5, dsum / cnt       # the bound of tests/test_engine_gpu.py::test_text_bf16x3_two_steps
+    for r in range(WORLD):
+        err = float(((res[r]["logits"].double() - logits[r]).norm(dim=1) / logits[r].norm(dim=1)).max())
+        assert err <= 1e-2, (r, err)      # logits AFTER one Adam step of +-lr per entry: trajectory bound, not the forward bound
