@@ -176,6 +176,15 @@ def test_wgrad_via_transposed_split_k(K, b, h, cin, cout, k):
     Bt = K.SView(torch.zeros(cout, 2 * ld, dtype=torch.bfloat16, device=DEV))
     K.im2col_transpose_split(X, b, h, h, cin, k, At)
     K.im2col_transpose_split(DZ, b, h, h, cout, 1, Bt)
+    # the transposes themselves are exact copies: At[(r, s, c), m] = X[pixel(m) + (r, s) - pad, c] plane by plane, zeros outside
+    pad = (k - 1) // 2
+    for plane in (0, 1):
+        src = X.base.view(M, 2 * cin)[:, plane * cin:(plane + 1) * cin].float().cpu().view(b, h, h, cin)
+        padded = F.pad(src, (0, 0, pad, pad, pad, pad))
+        want = torch.stack([padded[:, r:r + h, s_:s_ + h, :].reshape(M, cin) for r in range(k) for s_ in range(k)], 0)      # [taps, M, cin]
+        want = want.permute(0, 2, 1).reshape(k * k * cin, M)
+        got = At.base.view(k * k * cin, 2 * ld)[:, plane * ld:plane * ld + M].float().cpu()
+        assert torch.equal(got, want), ("plane", plane)
     dw = torch.zeros(k * k * cin, cout, device=DEV)
     K.gemm_bf16x3(At, Bt, K.View(dw), k=M, ksplit=4)
     close(dw, w.grad.reshape(-1, cout), 1e-4, "wgrad k=%d" % k)

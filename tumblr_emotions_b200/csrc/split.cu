@@ -647,7 +647,9 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
                                                                      uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
                                                                      int64_t ldo) {
   ds::pdl_enter();
-  __shared__ __align__(16) uint16_t th[64][72], tl[64][72];        // [m][c], rows padded to 144 bytes
+  // [m][c] tiles, 128-byte rows; the 16-byte channel group g of row m sits at group g ^ (m / 8 % 8): the transposed reads below
+  // (8 lanes = 8 row groups at one channel) then fall into 8 different 16-byte bank groups instead of one
+  __shared__ __align__(16) uint16_t th[64][64], tl[64][64];
   const int tap = blockIdx.z, r = tap / ks, s = tap - r * ks;
   const int64_t m0 = (int64_t)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
@@ -677,8 +679,9 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
         }
       }
     }
-    *reinterpret_cast<uint4*>(&th[mi][cj]) = vh;
-    *reinterpret_cast<uint4*>(&tl[mi][cj]) = vl;
+    const int sw = (((cj >> 3) ^ (mi >> 3)) & 7) << 3;
+    *reinterpret_cast<uint4*>(&th[mi][sw]) = vh;
+    *reinterpret_cast<uint4*>(&tl[mi][sw]) = vl;
   }
   __syncthreads();
   // store: thread -> (channel tid / 8 (+32), 8 pixels (tid % 8) * 8)
@@ -689,8 +692,9 @@ __global__ void __launch_bounds__(256) im2col_transpose_split_kernel(const uint1
     const int64_t m = m0 + mj;
     if (c < cin && m < M) {
       uint16_t eh[8], el[8];
+      const int col = ((((ci >> 3) ^ (mj >> 3)) & 7) << 3) | (ci & 7);      // rows mj .. mj+7 share one swizzle group
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { eh[e] = th[mj + e][ci]; el[e] = tl[mj + e][ci]; }
+      for (int e = 0; e < 8; ++e) { eh[e] = th[mj + e][col]; el[e] = tl[mj + e][col]; }
       const int64_t off = ((int64_t)tap * cin + c) * ldo + m;
       if (VEC) {      // rows are padded to a multiple of 8 pixels: the tail group stores zeros into the padding
         *reinterpret_cast<uint4*>(o_hi + off) = make_uint4(eh[0] | (eh[1] << 16), eh[2] | (eh[3] << 16), eh[4] | (eh[5] << 16), eh[6] | (eh[7] << 16));
