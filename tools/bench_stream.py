@@ -15,8 +15,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--reps", type=int, default=6)
 ap.add_argument("--only", default="")
+ap.add_argument("--debug", default="", help="key=value[,key=value]: launch-policy overrides of the development library (include/deepsent_dev.h)")
 args = ap.parse_args()
+if args.debug:
+    from tumblr_emotions_b200._lib import use_dev
+    _dev = use_dev(True)
 K.init(0)
+if args.debug:
+    for kv in args.debug.split(","):
+        _dev.debug_set(int(kv.split("=")[0]), int(kv.split("=")[1]))
 DEV, B = "cuda:0", args.batch
 NBUF = 2
 

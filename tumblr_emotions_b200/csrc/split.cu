@@ -488,7 +488,10 @@ __device__ __forceinline__ PoolRow pool_row_load(const uint16_t* __restrict__ x_
   return r;
 }
 
-__global__ void __launch_bounds__(256) maxpool_fwd_split_k3s1_walk_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
+// 3 CTAs per SM (80 registers, 8 bytes of spill) instead of the natural 2 (92 registers): 12-14 % faster on every in-block pool
+// (tools/bench_stream.py --only poolfwd); 4 per SM spills 100 bytes and is no faster than 2.  The same experiment on the batch-norm
+// and pool-backward kernels made them 20-60 % slower - they stay at their natural occupancy (profiles/r02_occupancy_variants.txt).
+__global__ void __launch_bounds__(256, 3) maxpool_fwd_split_k3s1_walk_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
                                                                           int64_t ldx, int64_t total, int h, int w, int c8, int hseg, int nseg,
                                                                           uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t ldy,
                                                                           uint8_t* __restrict__ argmax) {
