@@ -288,3 +288,53 @@ def test_results_do_not_depend_on_the_dependent_launch_policy(model, mode, monke
     assert row_rel_l2(fresh.get_logits(), want) <= 1e-3
     from tumblr_emotions_b200 import ops
     ops.dependent_launch(0)
+
+
+@pytest.mark.parametrize("model,mode", [("joint", "train"), ("image", "train"), ("joint", "infer")])
+def test_prefetched_batches_equal_synchronously_fed_ones(model, mode):
+    """The input pipeline of the trainers / forward runner (Engine.prefetch + commit_prefetch: the next batch's images are copied
+    from pinned host memory straight into the step's image buffer as soon as the stem's space-to-depth kernel - launched ahead of
+    the graph replay - has consumed the current ones; ids / lengths / labels go through staging buffers) must feed each step exactly
+    the batch a synchronous set_batch would: four different batches, graph replays back to back with no host synchronisation in
+    between, logits of every step and the final parameters compared with a second engine fed synchronously."""
+    train = mode == "train"
+    kw = {} if train else {"training": False}
+    a, p, _, mask = make(model, 4, "bf16x3", **kw)
+    b, _, _, _ = make(model, 4, "bf16x3", **kw)
+    batches = [O.synthetic_batch(4, seed=500 + i, vocab=VOCAB, with_images=True) for i in range(4)]
+    pinned = [{k: v.pin_memory() for k, v in bd.items()} for bd in batches]
+
+    def args_of(bd, eng):
+        return (bd["images"], bd["ids"] if eng.has_text else None, bd["seq_lens"] if eng.has_text else None, bd["labels"])
+
+    for eng in (a, b):
+        eng.set_batch(*args_of(batches[0], eng))
+        if train:
+            eng.capture()
+            eng.load_state_dict(p)
+            eng.adam_m.zero_(); eng.adam_v.zero_(); eng.adam_t = 0
+    step = (lambda e: e.train_step_graph(1e-3)) if train else (lambda e: e.forward_only())
+    # engine a: pipelined, never synchronising between steps
+    got = []
+    a.prefetch(*args_of(pinned[0], a))
+    for i in range(4):
+        a.commit_prefetch()
+        step(a)
+        if i + 1 < 4:
+            a.prefetch(*args_of(pinned[i + 1], a))
+        got.append(a.get_logits().clone())
+    torch.cuda.synchronize()
+    # engine b: one batch at a time
+    for i in range(4):
+        b.set_batch(*args_of(batches[i], b))
+        step(b)
+        torch.cuda.synchronize()
+        want = b.get_logits()
+        # step 0 (and every inference step): the same batch through the same kernels - equal to the rounding of the fp64-atomic BN
+        # sums.  Later training steps compare trajectories (Adam turns a rounding-level sign change of a near-zero gradient into a
+        # 2*lr parameter difference); a wrong or torn batch would move the logits by O(1).
+        tol = 1e-5 if (i == 0 or not train) else 5e-3
+        assert float((got[i] - want).abs().max()) <= tol * float(want.abs().max()), i
+    if train:
+        d = (a.params - b.params).abs()
+        assert float(d.max()) <= 2.1 * 4 * 1e-3 and float(d.mean()) <= 5e-5, (float(d.max()), float(d.mean()))      # run_steps' trajectory bound

@@ -144,6 +144,12 @@ class ConvUnit:
         return ops.bn_fwd_segment(View(self.Z).slice(c, n), self.stats[c:], self.N, self.mov_mean[c:c + n], self.mov_var[c:c + n],
                                   self.beta[c:c + n], self.mean[c:c + n], self.rstd[c:c + n], out)
 
+    def s2d(self):
+        """stem only: fp32 NHWC image -> space-to-depth split planes; the ONLY reader of the engine's image buffer, so the event
+        recorded behind it tells the input pipeline when the next batch's images may land there"""
+        ops.s2d_split(self.x.base, self.s2d_pitch, self.s2d_hi, self.s2d_lo)
+        self.eng._inputs_free.record()
+
     def fwd(self, train: bool, defer=()):
         """`defer`: output segments whose BN + ReLU the caller applies later in a grouped launch (train mode, split path)"""
         e, B, h = self.eng, self.eng.batch, self.h_in
@@ -160,7 +166,8 @@ class ConvUnit:
         if self.tc:
             ops.conv_bf16x3(self.x, B, h, h, self.cin, self.k, self.w_fwd, self.N, Zv, stats=self.stats if train else None)
         elif self.stem_tc:
-            ops.s2d_split(self.x.base, self.s2d_pitch, self.s2d_hi, self.s2d_lo)
+            if not e._s2d_external:       # graph replays run it ahead of the graph (Engine.stage_inputs)
+                self.s2d()
             ops.conv_s2d_rows(self.s2d_hi, self.s2d_lo, B, self.h_out, self.h_out, self.s2d_pitch, self.w_fwd, self.N, Zv,
                               stats=self.stats if train else None)
         else:
@@ -383,6 +390,7 @@ class Engine:
         self.dependent_launch, self.dependent_launch_side = int(pdl[0]), int(pdl[-1])
         self.blocks = {}                # first node of an inception block (its pool) -> (pool, u1, u2, u3, u4, group or None)
         self.comm, self.first_frozen_boundary, self.overlap_comm = None, None, False
+        self._s2d_external, self._inputs_free = False, torch.cuda.Event()
         self.z_override = None          # {scope: pre-activation [B,H,W,C], 'dense': [B, fc]} device tensors (tests only, eager mode)
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
@@ -427,6 +435,8 @@ class Engine:
         if self.has_text:
             self._build_text()
         self._build_head()
+        # the stem unit when it runs in space-to-depth form: the only reader of the image buffer (see stage_inputs / prefetch)
+        self._stem = self.units[0] if self.has_image and self.units and self.units[0].stem_tc else None
         self.init_params(seed)
 
     # -- memory ------------------------------------------------------------------------------------------------
@@ -1096,11 +1106,17 @@ class Engine:
         from ._lib import lib
         n0 = lib().launch_count()
         self._g1 = torch.cuda.CUDAGraph()
-        # thread_local: other threads of the process (torch.distributed's watchdog) may touch CUDA while this thread captures
-        with torch.cuda.graph(self._g1, stream=s, capture_error_mode="thread_local"):
-            self.fwd_bwd()
-            self.apply_gradients()
-        self.launches_per_step = lib().launch_count() - n0      # kernels of this library inside one captured step
+        # the one kernel that reads the raw image buffer stays OUTSIDE the graph (stage_inputs, launched right before each replay):
+        # the event behind it lets the next batch's host->device copy land in the image buffer while the step still runs
+        self._s2d_external = self._stem is not None
+        try:
+            # thread_local: other threads of the process (torch.distributed's watchdog) may touch CUDA while this thread captures
+            with torch.cuda.graph(self._g1, stream=s, capture_error_mode="thread_local"):
+                self.fwd_bwd()
+                self.apply_gradients()
+        finally:
+            self._s2d_external = False
+        self.launches_per_step = lib().launch_count() - n0 + (self._stem is not None)      # kernels of this library in one step
         self._graph = True
 
     def forward_only(self, train: bool = False):
@@ -1125,34 +1141,52 @@ class Engine:
             from ._lib import lib
             n0 = lib().launch_count()
             self._infer_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._infer_graph, stream=s, capture_error_mode="thread_local"):
-                self.forward(train=False)
-            self.infer_launches = lib().launch_count() - n0
+            self._s2d_external = self._stem is not None
+            try:
+                with torch.cuda.graph(self._infer_graph, stream=s, capture_error_mode="thread_local"):
+                    self.forward(train=False)
+            finally:
+                self._s2d_external = False
+            self.infer_launches = lib().launch_count() - n0 + (self._stem is not None)
+        self.stage_inputs()
         self._infer_graph.replay()
+
+    def stage_inputs(self):
+        """the part of a step that reads the raw image buffer (the stem's space-to-depth split), launched ahead of a graph replay"""
+        if self._stem is not None:
+            self._stem.s2d()
 
     def train_step_graph(self, lr: float):
         self.set_lr(lr)
+        self.stage_inputs()
         self._g1.replay()
         self.adam_t += 1
 
     # -- input pipeline ---------------------------------------------------------------------------------------
     def prefetch(self, images=None, ids=None, seq_lens=None, labels=None):
-        """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream into staging buffers, so
-        that it overlaps the step in flight; `commit_prefetch()` then moves it into the step's static input buffers with
-        device-to-device copies on the compute stream."""
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a copy stream so that it overlaps the step in
+        flight.  The images (154 MB at batch 256) go STRAIGHT into the step's image buffer: its only reader is the stem's
+        space-to-depth kernel at the very start of a step, and the copy waits for the event recorded behind that kernel.  The small
+        tensors (ids, lengths, labels are read throughout the step) go to staging buffers and `commit_prefetch()` moves them in."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._stage, self._stage_evt = {}, torch.cuda.Event()
+        direct = ("images",) if self._stem is not None else ()
         with torch.cuda.stream(self._copy_stream):
             for name, src in (("images", images), ("ids", ids), ("seq_lens", seq_lens), ("labels", labels)):
                 if src is None:
                     continue
                 dst = getattr(self, name)
+                if name in direct:
+                    self._copy_stream.wait_event(self._inputs_free)
+                    dst.copy_(src, non_blocking=True)
+                    continue
                 if name not in self._stage:
                     self._stage[name] = torch.empty_like(dst)
                 self._stage[name].copy_(src, non_blocking=True)
             self._stage_evt.record(self._copy_stream)
-        self._staged = [n for n, v in (("images", images), ("ids", ids), ("seq_lens", seq_lens), ("labels", labels)) if v is not None]
+        self._staged = [n for n, v in (("images", images), ("ids", ids), ("seq_lens", seq_lens), ("labels", labels))
+                        if v is not None and n not in direct]
 
     def commit_prefetch(self):
         cur = torch.cuda.current_stream()
