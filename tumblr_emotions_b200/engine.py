@@ -736,12 +736,13 @@ class Engine:
             if self.split:
                 ld = (T * B + 7) // 8 * 8
                 self.DZs = self.new_split((T, B), 4 * n)
-                self.HsT = SView(self.new_split((n,), ld))                   # time-major (K-major) operands of the weight gradients
+                # time-major (K-major) operands of the weight gradients.  [E^T ; H^T ; 1] stacked in the row order of the LSTM kernel
+                # variable ([x ; h] rows) followed by a row of ones: ONE GEMM against dZ^T then yields d(kernel) and, from the last
+                # row, d(bias) (the column sums of dZ), written straight into the gradient arena where the two are adjacent
+                self.XHT = SView(self.new_split((self.emb_dim + n + 1,), ld))
+                self.EsT, self.HsT = self.XHT.rows_slice(0, self.emb_dim), self.XHT.rows_slice(self.emb_dim, n)
+                self.XHT.base.view(self.emb_dim + n + 1, 2 * ld)[self.emb_dim + n, :T * B] = 1.0
                 self.DZsT = SView(self.new_split((4 * n,), ld))
-                # [E^T ; 1]: the extra row of ones makes the same GEMM produce the bias gradient (column sums of dZ)
-                self.EsT = SView(self.new_split((self.emb_dim + 1,), ld))
-                self.EsT.base.view(self.emb_dim + 1, 2 * ld)[self.emb_dim, :T * B] = 1.0
-                self._dke = self.new(self.emb_dim + 1, 4 * n)
             else:
                 self.DZ = self.new(T * B, 4 * n)
 
@@ -790,20 +791,26 @@ class Engine:
             TB = T * B
             ops.im2col_transpose_split(SView(self.DZs), TB, 1, 1, 4 * n, 1, self.DZsT)
             ops.im2col_transpose_split(SView(self.Hs[:T]), TB, 1, 1, n, 1, self.HsT)
-            ops.im2col_transpose_split(self.Es, TB, 1, 1, e, 1, self.EsT.rows_slice(0, e))
-            dk.zero_()
-            self._dke.zero_()
+            ops.im2col_transpose_split(self.Es, TB, 1, 1, e, 1, self.EsT)
+            dkb = self._lstm_grad_block()           # [e + n + 1, 4n]: d(kernel) rows followed by the d(bias) row
+            dkb.zero_()
             chunks = -(-TB // 64)
-            ks = max(1, min(chunks, -(-2 * self.sm_count // (-(-n // 128) * -(-4 * n // 256)))))
-            ops.gemm_bf16x3(self.HsT, self.DZsT, View(dk[e:]), k=TB, ksplit=ks)
-            ks = max(1, min(chunks, -(-2 * self.sm_count // -(-4 * n // 256))))
-            ops.gemm_bf16x3(self.EsT, self.DZsT, View(self._dke), k=TB, ksplit=ks)
-            ops.copy2d(View(self._dke[:e]), View(dk[:e]))
-            ops.copy2d(View(self._dke[e:]), View(self.grad("Text/rnn/basic_lstm_cell/bias").view(1, 4 * n)))
+            ks = max(1, min(chunks, -(-2 * self.sm_count // (-(-(e + n + 1) // 128) * -(-4 * n // 256)))))
+            ops.gemm_bf16x3(self.XHT, self.DZsT, View(dkb), k=TB, ksplit=ks)
         else:
             ops.gemm_tn(View(self.E, e), View(self.DZ), View(dk[:e]))
             ops.gemm_tn(View(self.H[:T].view(T * B, n)), View(self.DZ), View(dk[e:]))
             ops.colsum(View(self.DZ), self.grad("Text/rnn/basic_lstm_cell/bias"))
+
+    def _lstm_grad_block(self):
+        """d(kernel) and d(bias) of the LSTM cell as one [emb + n + 1, 4n] matrix inside the gradient arena (the parameter table
+        lays the bias out right behind the kernel)"""
+        dk, db = self.grad("Text/rnn/basic_lstm_cell/kernel"), self.grad("Text/rnn/basic_lstm_cell/bias")
+        rows, cols = dk.shape
+        if dk.data_ptr() + dk.numel() * 4 != db.data_ptr() or db.numel() != cols:
+            raise RuntimeError("gradient arena: the LSTM bias gradient must follow the kernel gradient")
+        off = (dk.data_ptr() - self.grads.data_ptr()) // 4
+        return self.grads[off:off + (rows + 1) * cols].view(rows + 1, cols)
 
     # -- head ------------------------------------------------------------------------------------------------
     def _build_head(self):
